@@ -1,0 +1,98 @@
+// Shared host-side plumbing of libdatmo_b200: the handle, its workspace arena,
+// launch bookkeeping and per-tag event timing.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/datmo_b200.h"
+
+struct datmo_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    // grow-only workspace
+    char* ws = nullptr;
+    size_t ws_cap = 0;
+    // small pinned staging area for host-returning calls
+    char* pinned = nullptr;
+    size_t pinned_cap = 0;
+    std::string err;
+    // profiling
+    bool prof = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<std::pair<int, int>> ev_used;  // (tag, pool index)
+    int64_t prof_launches[DATMO_TAG_COUNT] = {0};
+    double prof_ms[DATMO_TAG_COUNT] = {0};
+    int64_t launches = 0;
+};
+
+#define DATMO_CHECK_CUDA(h, expr)                                                              \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            char _buf[512];                                                                    \
+            snprintf(_buf, sizeof(_buf), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,         \
+                     cudaGetErrorString(_e));                                                  \
+            (h)->err = _buf;                                                                   \
+            return DATMO_E_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define DATMO_REQUIRE(h, cond, msg)                  \
+    do {                                             \
+        if (!(cond)) {                               \
+            (h)->err = std::string("invalid: ") + (msg); \
+            return DATMO_E_INVALID;                  \
+        }                                            \
+    } while (0)
+
+#define DATMO_ENTER(h)                                   \
+    do {                                                 \
+        if (!(h)) return DATMO_E_INVALID;                \
+        DATMO_CHECK_CUDA(h, cudaSetDevice((h)->device)); \
+    } while (0)
+
+#define DATMO_TRY(expr)              \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != DATMO_OK) return _s; \
+    } while (0)
+
+// Bump sub-allocator over the handle's workspace.  Run once with base == nullptr to
+// size the arena, then again over the real buffer.
+struct Bump {
+    char* base;
+    size_t off = 0;
+    explicit Bump(char* b) : base(b) {}
+    template <typename T>
+    T* take(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+
+int datmo_ws_reserve(datmo_ctx* h, size_t bytes);
+int datmo_pinned_reserve(datmo_ctx* h, size_t bytes);
+
+// RAII-ish bracket around a kernel launch: counts it and, when profiling is on,
+// records an event pair on the handle's stream.
+struct LaunchScope {
+    datmo_ctx* h;
+    int idx = -1;
+    LaunchScope(datmo_ctx* h_, int tag, int n_launches = 1);
+    ~LaunchScope();
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+#define DATMO_POST_LAUNCH(h) DATMO_CHECK_CUDA(h, cudaGetLastError())

@@ -1,0 +1,431 @@
+// DBSCAN over the (row, col, vx, vy) features of the valid BEV cells, as a grid
+// union-find, plus the per-cluster summaries.  sm_100a.
+//
+// Replaces dbscan_clustering (Optical_flow/main.py:231-259: sklearn.cluster.DBSCAN on
+// the row-major list of valid cells) and extract_cluster_data (main.py:402-434).
+// sklearn's result is reproduced exactly, numbering included, by the grid rule of
+// SURVEY.md §8 a8 (restated in oracle/dbscan_np.py):
+//   neighbours    valid cells of the (2*floor(eps)+1)^2 window with
+//                 d2 = drow^2 + dcol^2 + dvx^2 + dvy^2 <= eps^2 in fp64, that summation
+//                 order, every operation rounded (no FMA); self included
+//   core          neighbour count >= min_samples
+//   clusters      connected components of core cells; root = MINIMUM row-major index
+//   border cell   takes the smallest root among its core neighbours, else noise (-1)
+//   label         rank of the root among all roots in ascending order
+// Row-major ranks (the order of np.nonzero) come from a flag scan of the grid.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SCAN_ITEMS = 4096;  // grid cells handled by one CTA of the flag scan
+constexpr int SCAN_THREADS = 256;
+
+// ---- generic exclusive scan of uint8 flags over [batch][n] ---------------------------
+// pass 1: per-CTA totals
+__global__ void __launch_bounds__(SCAN_THREADS) k_flag_block_sums(const uint8_t* __restrict__ flags, int64_t n,
+                                                                  int nblk, int32_t* __restrict__ block_sums) {
+    const int blk = blockIdx.x, b = blockIdx.y;
+    const uint8_t* f = flags + static_cast<size_t>(b) * n;
+    int64_t start = static_cast<int64_t>(blk) * SCAN_ITEMS;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < SCAN_ITEMS; i += SCAN_THREADS) {
+        int64_t p = start + i;
+        cnt += (p < n) ? (f[p] != 0) : 0;
+    }
+    __shared__ int s_w[SCAN_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < SCAN_THREADS / 32; ++i) t += s_w[i];
+        block_sums[static_cast<size_t>(b) * nblk + blk] = t;
+    }
+}
+
+// pass 2: one CTA per frame turns the CTA totals into exclusive offsets and the total
+__global__ void __launch_bounds__(256) k_scan_block_sums(int32_t* __restrict__ block_sums, int nblk,
+                                                         int32_t* __restrict__ totals) {
+    const int b = blockIdx.x;
+    int32_t* s = block_sums + static_cast<size_t>(b) * nblk;
+    __shared__ int s_part[256];
+    // each thread owns a contiguous run
+    int per = (nblk + 255) / 256;
+    int lo = threadIdx.x * per, hi = min(lo + per, nblk);
+    int t = 0;
+    for (int i = lo; i < hi; ++i) t += s[i];
+    s_part[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < 256; ++i) {
+            int v = s_part[i];
+            s_part[i] = run;
+            run += v;
+        }
+        totals[b] = run;
+    }
+    __syncthreads();
+    int run = s_part[threadIdx.x];
+    for (int i = lo; i < hi; ++i) {
+        int v = s[i];
+        s[i] = run;
+        run += v;
+    }
+}
+
+// pass 3: exclusive rank of every flagged cell (others get -1)
+__global__ void __launch_bounds__(SCAN_THREADS) k_flag_ranks(const uint8_t* __restrict__ flags, int64_t n, int nblk,
+                                                             const int32_t* __restrict__ block_offs,
+                                                             int32_t* __restrict__ rank) {
+    const int blk = blockIdx.x, b = blockIdx.y;
+    const uint8_t* f = flags + static_cast<size_t>(b) * n;
+    int32_t* r = rank + static_cast<size_t>(b) * n;
+    const int64_t start = static_cast<int64_t>(blk) * SCAN_ITEMS;
+    constexpr int PER = SCAN_ITEMS / SCAN_THREADS;  // contiguous cells per thread
+    const int64_t p0 = start + static_cast<int64_t>(threadIdx.x) * PER;
+    int local[PER];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int64_t p = p0 + i;
+        local[i] = (p < n) ? (f[p] != 0) : 0;
+        cnt += local[i];
+    }
+    // CTA-wide exclusive scan of cnt
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    __shared__ int s_w[SCAN_THREADS / 32];
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < wid; ++i) woff += s_w[i];
+    int run = block_offs[static_cast<size_t>(b) * nblk + blk] + woff + inc - cnt;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int64_t p = p0 + i;
+        if (p < n) {
+            r[p] = local[i] ? run : -1;
+            run += local[i];
+        }
+    }
+}
+
+// ---- neighbour predicate ----------------------------------------------------------------
+__device__ __forceinline__ bool within_eps(int dr, int dc, float vx0, float vy0, float vx1, float vy1, double eps2) {
+    double d2 = static_cast<double>(dr * dr);
+    d2 = __dadd_rn(d2, static_cast<double>(dc * dc));
+    const double dvx = __dsub_rn(static_cast<double>(vx0), static_cast<double>(vx1));
+    const double dvy = __dsub_rn(static_cast<double>(vy0), static_cast<double>(vy1));
+    d2 = __dadd_rn(d2, __dmul_rn(dvx, dvx));
+    d2 = __dadd_rn(d2, __dmul_rn(dvy, dvy));
+    return d2 <= eps2;
+}
+
+// state: 0 = not valid, 1 = valid non-core, 2 = core.  parent: self for core cells, -1 otherwise.
+__global__ void __launch_bounds__(256) k_core(const float* __restrict__ vx, const float* __restrict__ vy,
+                                              const uint8_t* __restrict__ valid, int H, int W, int r, double eps2,
+                                              int min_samples, uint8_t* __restrict__ state,
+                                              int32_t* __restrict__ parent) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const int o = y * W + x;
+    uint8_t st = 0;
+    if (valid[base + o]) {
+        const float vx0 = vx[base + o], vy0 = vy[base + o];
+        int cnt = 0;
+        for (int dr = -r; dr <= r && cnt < min_samples; ++dr) {
+            int yy = y + dr;
+            if (yy < 0 || yy >= H) continue;
+            for (int dc = -r; dc <= r; ++dc) {
+                int xx = x + dc;
+                if (xx < 0 || xx >= W) continue;
+                size_t q = base + static_cast<size_t>(yy) * W + xx;
+                if (valid[q] && within_eps(dr, dc, vx0, vy0, vx[q], vy[q], eps2)) ++cnt;
+            }
+        }
+        st = cnt >= min_samples ? 2 : 1;
+    }
+    state[base + o] = st;
+    parent[base + o] = st == 2 ? o : -1;
+}
+
+// Union-find over int32 cell indices.  Other CTAs link roots concurrently, and L1 is not
+// coherent between SMs, so every read of the forest goes to L2 (__ldcg) and every link is
+// an atomicCAS; a stale L1 line could otherwise make a thread retry the same CAS forever.
+__device__ __forceinline__ int uf_find(int32_t* parent, int a) {
+    int p = __ldcg(parent + a);
+    while (p != a) {
+        int gp = __ldcg(parent + p);
+        if (gp != p) __stcg(parent + a, gp);  // path halving; only ever shortens the path
+        a = p;
+        p = gp;
+    }
+    return a;
+}
+
+__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            int t = a;
+            a = b;
+            b = t;
+        }
+        // a > b: hang the larger root under the smaller, so a root is always the
+        // minimum index of its component
+        int old = atomicCAS(parent + a, a, b);
+        if (old == a) return;
+        a = old;  // someone linked a first; continue from where it points now
+    }
+}
+
+__global__ void __launch_bounds__(256) k_union(const float* __restrict__ vx, const float* __restrict__ vy,
+                                               const uint8_t* __restrict__ state, int H, int W, int r, double eps2,
+                                               int32_t* __restrict__ parent) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const int o = y * W + x;
+    if (state[base + o] != 2) return;
+    const float vx0 = vx[base + o], vy0 = vy[base + o];
+    int32_t* par = parent + base;
+    // each unordered pair once: only neighbours that precede this cell in row-major order
+    for (int dr = -r; dr <= 0; ++dr) {
+        int yy = y + dr;
+        if (yy < 0) continue;
+        int dc_hi = dr == 0 ? -1 : r;
+        for (int dc = -r; dc <= dc_hi; ++dc) {
+            int xx = x + dc;
+            if (xx < 0 || xx >= W) continue;
+            int q = yy * W + xx;
+            if (state[base + q] == 2 && within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2))
+                uf_union(par, o, q);
+        }
+    }
+}
+
+// flatten + mark roots
+__global__ void __launch_bounds__(256) k_flatten(const uint8_t* __restrict__ state, int64_t n,
+                                                 int32_t* __restrict__ parent, uint8_t* __restrict__ is_root) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= n) return;
+    const size_t base = static_cast<size_t>(b) * n;
+    uint8_t root = 0;
+    if (state[base + i] == 2) {
+        int a = static_cast<int>(i);
+        int32_t* par = parent + base;
+        int p = par[a];
+        while (p != par[p]) p = par[p];
+        // all unions are finished (previous kernel), so this write cannot race with a link
+        par[a] = p;
+        root = p == a;
+    }
+    is_root[base + i] = root;
+}
+
+__global__ void __launch_bounds__(256) k_labels(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                const uint8_t* __restrict__ state, const int32_t* __restrict__ parent,
+                                                const int32_t* __restrict__ rank, const int32_t* __restrict__ root_rank,
+                                                int H, int W, int r, double eps2, int cap,
+                                                int32_t* __restrict__ labels, int32_t* __restrict__ indices) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const int o = y * W + x;
+    const uint8_t st = state[base + o];
+    if (st == 0) return;
+    const int slot = rank[base + o];
+    if (slot >= cap) return;
+    int root = -1;
+    if (st == 2) {
+        root = parent[base + o];
+    } else {
+        const float vx0 = vx[base + o], vy0 = vy[base + o];
+        for (int dr = -r; dr <= r; ++dr) {
+            int yy = y + dr;
+            if (yy < 0 || yy >= H) continue;
+            for (int dc = -r; dc <= r; ++dc) {
+                int xx = x + dc;
+                if (xx < 0 || xx >= W) continue;
+                int q = yy * W + xx;
+                if (state[base + q] == 2 && within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2)) {
+                    int rt = parent[base + q];
+                    if (root < 0 || rt < root) root = rt;
+                }
+            }
+        }
+    }
+    const size_t out = static_cast<size_t>(b) * cap + slot;
+    labels[out] = root >= 0 ? root_rank[base + root] : -1;
+    indices[2 * out] = y;
+    indices[2 * out + 1] = x;
+}
+
+int flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, int32_t* block_sums, int32_t* totals,
+              int32_t* rank, int tag) {
+    int nblk = static_cast<int>(ceil_div64(n, SCAN_ITEMS));
+    dim3 g(nblk, batch);
+    {
+        LaunchScope ls(h, tag);
+        k_flag_block_sums<<<g, SCAN_THREADS, 0, h->stream>>>(flags, n, nblk, block_sums);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, tag);
+        k_scan_block_sums<<<batch, 256, 0, h->stream>>>(block_sums, nblk, totals);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, tag);
+        k_flag_ranks<<<g, SCAN_THREADS, 0, h->stream>>>(flags, n, nblk, block_sums, rank);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+// ---- cluster summaries ------------------------------------------------------------------------
+// acc: double [batch][max_clusters][8] = n, sum r, sum c, sum vx, sum vy, sum rr, sum rc, sum cc
+__global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                       int H, int W, int cap, const int32_t* __restrict__ n_valid,
+                                                       const int32_t* __restrict__ labels,
+                                                       const int32_t* __restrict__ indices, int max_clusters,
+                                                       double* __restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const int n = min(n_valid[b], cap);
+    if (i >= n) return;
+    const size_t o = static_cast<size_t>(b) * cap + i;
+    const int lab = labels[o];
+    if (lab < 0 || lab >= max_clusters) return;
+    const int r = indices[2 * o], c = indices[2 * o + 1];
+    const size_t p = (static_cast<size_t>(b) * H + r) * W + c;
+    double* a = acc + (static_cast<size_t>(b) * max_clusters + lab) * 8;
+    const double dr = r, dc = c;
+    atomicAdd(a + 0, 1.0);
+    atomicAdd(a + 1, dr);
+    atomicAdd(a + 2, dc);
+    atomicAdd(a + 3, static_cast<double>(vx[p]));
+    atomicAdd(a + 4, static_cast<double>(vy[p]));
+    atomicAdd(a + 5, dr * dr);
+    atomicAdd(a + 6, dr * dc);
+    atomicAdd(a + 7, dc * dc);
+}
+
+__global__ void __launch_bounds__(256) k_cluster_finalize(int total, double* __restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    double* a = acc + static_cast<size_t>(i) * 8;
+    const double n = a[0];
+    if (n <= 0) return;
+    const double mr = a[1] / n, mc = a[2] / n;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    // row / col sums are exact integers in fp64, so the one-pass covariance is exact up to the final divisions
+    const double crr = n > 1 ? (a[5] - a[1] * a[1] / n) / (n - 1) : nan;
+    const double crc = n > 1 ? (a[6] - a[1] * a[2] / n) / (n - 1) : nan;
+    const double ccc = n > 1 ? (a[7] - a[2] * a[2] / n) / (n - 1) : nan;
+    a[1] = mr;
+    a[2] = mc;
+    a[3] = a[3] / n;
+    a[4] = a[4] / n;
+    a[5] = crr;
+    a[6] = crc;
+    a[7] = ccc;
+}
+
+}  // namespace
+
+extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const float* vy_f, const uint8_t* valid,
+                                     int H, int W, int batch, double eps, int min_samples, int cap, int32_t* n_valid,
+                                     int32_t* labels, int32_t* indices, int32_t* n_clusters) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, vx_f && vy_f && valid && n_valid && labels && indices, "null pointer");
+    DATMO_REQUIRE(h, H >= 1 && W >= 1 && batch >= 1 && cap >= 1, "bad sizes");
+    DATMO_REQUIRE(h, static_cast<int64_t>(H) * W < (int64_t(1) << 31), "grid too large for int32 cell indices");
+    DATMO_REQUIRE(h, H <= 65535 && batch <= 65535, "H and batch must fit a CUDA grid dimension");
+    DATMO_REQUIRE(h, eps >= 0 && eps < 1024 && min_samples >= 1, "eps / min_samples out of range");
+    const int64_t n = static_cast<int64_t>(H) * W;
+    const int nblk = static_cast<int>(ceil_div64(n, SCAN_ITEMS));
+    const int r = static_cast<int>(floor(eps));
+    const double eps2 = eps * eps;
+    size_t total;
+    uint8_t *state, *is_root;
+    int32_t *parent, *rank, *root_rank, *bsum, *ncl;
+    for (int pass = 0; pass < 2; ++pass) {
+        Bump bump(pass ? h->ws : nullptr);
+        state = bump.take<uint8_t>(batch * n);
+        is_root = bump.take<uint8_t>(batch * n);
+        parent = bump.take<int32_t>(batch * n);
+        rank = bump.take<int32_t>(batch * n);
+        root_rank = bump.take<int32_t>(batch * n);
+        bsum = bump.take<int32_t>(static_cast<size_t>(batch) * nblk);
+        ncl = bump.take<int32_t>(batch);
+        total = bump.off;
+        if (!pass) DATMO_TRY(datmo_ws_reserve(h, total));
+    }
+    DATMO_TRY(flag_scan(h, valid, n, batch, bsum, n_valid, rank, DATMO_TAG_DBSCAN));
+    dim3 g(ceil_div(W, 256), H, batch);
+    {
+        LaunchScope ls(h, DATMO_TAG_DBSCAN);
+        k_core<<<g, 256, 0, h->stream>>>(vx_f, vy_f, valid, H, W, r, eps2, min_samples, state, parent);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, DATMO_TAG_DBSCAN);
+        k_union<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, DATMO_TAG_DBSCAN);
+        dim3 gf(static_cast<unsigned>(ceil_div64(n, 256)), batch);
+        k_flatten<<<gf, 256, 0, h->stream>>>(state, n, parent, is_root);
+    }
+    DATMO_POST_LAUNCH(h);
+    int32_t* ncl_out = n_clusters ? n_clusters : ncl;
+    DATMO_TRY(flag_scan(h, is_root, n, batch, bsum, ncl_out, root_rank, DATMO_TAG_DBSCAN));
+    {
+        LaunchScope ls(h, DATMO_TAG_DBSCAN);
+        k_labels<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, parent, rank, root_rank, H, W, r, eps2, cap, labels,
+                                           indices);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+extern "C" int datmo_cluster_summary_dev(datmo_handle_t h, const float* vx_f, const float* vy_f, int H, int W,
+                                         int batch, int cap, const int32_t* n_valid, const int32_t* labels,
+                                         const int32_t* indices, int max_clusters, double* summary) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, vx_f && vy_f && n_valid && labels && indices && summary, "null pointer");
+    DATMO_REQUIRE(h, H >= 1 && W >= 1 && batch >= 1 && cap >= 1 && max_clusters >= 1, "bad sizes");
+    DATMO_REQUIRE(h, batch <= 65535, "batch must fit a CUDA grid dimension");
+    const size_t total = static_cast<size_t>(batch) * max_clusters;
+    DATMO_CHECK_CUDA(h, cudaMemsetAsync(summary, 0, total * 8 * sizeof(double), h->stream));
+    {
+        LaunchScope ls(h, DATMO_TAG_CLUSTER);
+        dim3 g(ceil_div(cap, 256), batch);
+        k_cluster_accum<<<g, 256, 0, h->stream>>>(vx_f, vy_f, H, W, cap, n_valid, labels, indices, max_clusters,
+                                                  summary);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, DATMO_TAG_CLUSTER);
+        k_cluster_finalize<<<ceil_div(static_cast<int>(total), 256), 256, 0, h->stream>>>(static_cast<int>(total),
+                                                                                          summary);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}

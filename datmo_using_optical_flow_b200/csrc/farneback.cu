@@ -1,0 +1,849 @@
+// Dense Farneback optical flow for batches of BEV frame pairs, sm_100a.
+//
+// Replaces cv2.calcOpticalFlowFarneback as the reference calls it at
+// Optical_flow/main.py:131-142 (flags = 0: box window, no initial flow).  The
+// algorithm (OpenCV video/optflowgf.cpp) is re-derived for
+// the GPU, not transcribed:
+//   * the pyramid image of a layer is evaluated directly at the resized resolution:
+//     the separable Gaussian is applied only at the source taps the bilinear resize
+//     reads (k_pyr_h, k_pyr_v), instead of blurring the full-resolution frame;
+//   * polynomial expansion is one tiled kernel, both separable passes staged through
+//     shared memory (k_polyexp), for prev and next frames of the whole batch at once;
+//   * one flow iteration = updateMatrices + 5-channel box blur + 2x2 solve is ONE
+//     kernel (k_flow_iter<true>): the M field never exists in global memory;
+//   * all arrays are planar [batch][channel][h][w] f32 so every warp access is a
+//     contiguous 128-byte line; flow is float2 per pixel.
+// Arithmetic is f32 with direct (non-running) window sums, which SURVEY.md §3.2 F6
+// and tests/test_oracle_farneback.py show stays inside the parity tolerance.
+#include <math.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// host-side plan (F0 / F1)
+// ------------------------------------------------------------------------------------
+struct FbLayer {
+    int k;
+    double scale, sigma;
+    int ksize, w, h;
+};
+
+inline int cv_round(double v) { return static_cast<int>(nearbyint(v)); }  // round half to even
+
+std::vector<FbLayer> fb_plan(int H, int W, double pyr_scale, int levels) {
+    const int min_size = 32;
+    int k = 0;
+    double scale = 1.0;
+    while (k < levels) {
+        scale *= pyr_scale;
+        if (W * scale < min_size || H * scale < min_size) break;
+        ++k;
+    }
+    std::vector<FbLayer> out;
+    for (int kk = k; kk >= 0; --kk) {
+        double s = 1.0;
+        for (int i = 0; i < kk; ++i) s *= pyr_scale;
+        FbLayer L;
+        L.k = kk;
+        L.scale = s;
+        L.sigma = (1.0 / s - 1.0) * 0.5;
+        L.ksize = std::max(cv_round(L.sigma * 5) | 1, 3);
+        L.w = cv_round(W * s);
+        L.h = cv_round(H * s);
+        out.push_back(L);
+    }
+    return out;
+}
+
+std::vector<float> gaussian_kernel(int ksize, double sigma) {
+    std::vector<float> k(ksize);
+    if (sigma <= 0 && ksize == 3) {
+        k[0] = 0.25f, k[1] = 0.5f, k[2] = 0.25f;
+        return k;
+    }
+    if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+    std::vector<double> t(ksize);
+    double sum = 0;
+    for (int i = 0; i < ksize; ++i) {
+        double x = i - (ksize - 1) * 0.5;
+        t[i] = exp(-0.5 / (sigma * sigma) * x * x);
+        sum += t[i];
+    }
+    for (int i = 0; i < ksize; ++i) k[i] = static_cast<float>(t[i] / sum);
+    return k;
+}
+
+constexpr int POLY_MAX_N = 16;
+struct PolyCoef {
+    float g[POLY_MAX_N + 1], xg[POLY_MAX_N + 1], xxg[POLY_MAX_N + 1];
+    float ig11, ig03, ig33, ig55;
+    int n;
+};
+
+bool invert6(double a[6][6], double inv[6][6]) {
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) inv[i][j] = i == j;
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+        if (a[piv][c] == 0) return false;
+        for (int j = 0; j < 6; ++j) {
+            std::swap(a[c][j], a[piv][j]);
+            std::swap(inv[c][j], inv[piv][j]);
+        }
+        double d = 1.0 / a[c][c];
+        for (int j = 0; j < 6; ++j) {
+            a[c][j] *= d;
+            inv[c][j] *= d;
+        }
+        for (int r = 0; r < 6; ++r) {
+            if (r == c) continue;
+            double f = a[r][c];
+            if (f == 0) continue;
+            for (int j = 0; j < 6; ++j) {
+                a[r][j] -= f * a[c][j];
+                inv[r][j] -= f * inv[c][j];
+            }
+        }
+    }
+    return true;
+}
+
+bool poly_setup(int n, double sigma, PolyCoef& pc) {
+    if (n < 1 || n > POLY_MAX_N) return false;
+    if (sigma < 1.1920928955078125e-07) sigma = n * 0.3;
+    std::vector<float> g(2 * n + 1), xg(2 * n + 1), xxg(2 * n + 1);
+    double s = 0;
+    for (int x = -n; x <= n; ++x) {
+        g[x + n] = static_cast<float>(exp(-x * x / (2 * sigma * sigma)));
+        s += g[x + n];
+    }
+    s = 1.0 / s;
+    for (int x = -n; x <= n; ++x) {
+        g[x + n] = static_cast<float>(g[x + n] * s);
+        xg[x + n] = static_cast<float>(x * g[x + n]);
+        xxg[x + n] = static_cast<float>(x * x * g[x + n]);
+    }
+    double G[6][6] = {{0}};
+    for (int y = -n; y <= n; ++y)
+        for (int x = -n; x <= n; ++x) {
+            float gg = g[y + n] * g[x + n];
+            G[0][0] += gg;
+            G[1][1] += gg * x * x;
+            G[3][3] += gg * x * x * x * x;
+            G[5][5] += gg * x * x * y * y;
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    double inv[6][6];
+    if (!invert6(G, inv)) return false;
+    pc.n = n;
+    for (int k = 0; k <= n; ++k) {
+        pc.g[k] = g[n + k];
+        pc.xg[k] = xg[n + k];
+        pc.xxg[k] = xxg[n + k];
+    }
+    pc.ig11 = static_cast<float>(inv[1][1]);
+    pc.ig03 = static_cast<float>(inv[0][3]);
+    pc.ig33 = static_cast<float>(inv[3][3]);
+    pc.ig55 = static_cast<float>(inv[5][5]);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+// INTER_LINEAR source tap of destination index d (F2): src = (d+0.5)*S/D - 0.5 in
+// fp64 with every operation rounded, then the two clamp rules.
+__device__ __forceinline__ void resize_tap(int d, int S, double ratio, int& s, double& f) {
+    double src = __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(d), 0.5), ratio), -0.5);
+    double fl = floor(src);
+    s = static_cast<int>(fl);
+    f = src - fl;
+    if (s < 0) s = 0, f = 0;
+    if (s >= S - 1) s = S - 1, f = 0;
+}
+
+__device__ __forceinline__ float load_px(const uint8_t* p) { return static_cast<float>(*p); }
+__device__ __forceinline__ float load_px(const float* p) { return *p; }
+
+// ------------------------------------------------------------------------------------
+// F2: pyramid image.  Horizontal Gaussian + horizontal resize, then vertical Gaussian
+// + vertical resize; the blur is only evaluated at the taps the resize reads.
+// ------------------------------------------------------------------------------------
+template <typename SrcT>
+__global__ void __launch_bounds__(128) k_pyr_h(const SrcT* __restrict__ src, float* __restrict__ T, int H, int W,
+                                               int w, const float* __restrict__ kern, int ksize, double ratio) {
+    int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    int b = blockIdx.z;
+    if (dx >= w) return;
+    int sx;
+    double fx;
+    resize_tap(dx, W, ratio, sx, fx);
+    const SrcT* row = src + (static_cast<size_t>(b) * H + y) * W;
+    int r = ksize >> 1;
+    float a0 = 0.f, a1 = 0.f;
+    if (sx - r >= 0 && sx + 1 + r < W) {
+        const SrcT* p = row + sx - r;
+        for (int i = 0; i < ksize; ++i) {
+            float kv = kern[i];
+            a0 = fmaf(kv, load_px(p + i), a0);
+            a1 = fmaf(kv, load_px(p + i + 1), a1);
+        }
+    } else {
+        for (int i = 0; i < ksize; ++i) {
+            float kv = kern[i];
+            a0 = fmaf(kv, load_px(row + reflect101(sx + i - r, W)), a0);
+            a1 = fmaf(kv, load_px(row + reflect101(sx + 1 + i - r, W)), a1);
+        }
+    }
+    float v = fx == 0.0 ? a0 : static_cast<float>((1.0 - fx) * a0 + fx * a1);
+    T[(static_cast<size_t>(b) * H + y) * w + dx] = v;
+}
+
+__global__ void __launch_bounds__(128) k_pyr_v(const float* __restrict__ T, float* __restrict__ out, int H, int w,
+                                               int h, const float* __restrict__ kern, int ksize, double ratio) {
+    int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    int dy = blockIdx.y;
+    int b = blockIdx.z;
+    if (dx >= w) return;
+    int sy;
+    double fy;
+    resize_tap(dy, H, ratio, sy, fy);
+    const float* base = T + static_cast<size_t>(b) * H * w + dx;
+    int r = ksize >> 1;
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = 0; i < ksize; ++i) {
+        float kv = kern[i];
+        a0 = fmaf(kv, base[static_cast<size_t>(reflect101(sy + i - r, H)) * w], a0);
+        a1 = fmaf(kv, base[static_cast<size_t>(reflect101(sy + 1 + i - r, H)) * w], a1);
+    }
+    float v = fy == 0.0 ? a0 : static_cast<float>((1.0 - fy) * a0 + fy * a1);
+    out[(static_cast<size_t>(b) * h + dy) * w + dx] = v;
+}
+
+// ------------------------------------------------------------------------------------
+// F4: polynomial expansion, one tile per CTA, both passes through shared memory
+// ------------------------------------------------------------------------------------
+constexpr int PE_TX = 32, PE_TY = 16, PE_THREADS = 256;
+
+__global__ void __launch_bounds__(PE_THREADS) k_polyexp(const float* __restrict__ I, float* __restrict__ R, int w,
+                                                        int h, PolyCoef pc) {
+    extern __shared__ float smem[];
+    const int n = pc.n;
+    const int RW = PE_TX + 2 * n, RH = PE_TY + 2 * n;
+    float* sI = smem;                  // [RH][RW]
+    float* sr0 = sI + RH * RW;         // [PE_TY][RW] x3
+    float* sr1 = sr0 + PE_TY * RW;
+    float* sr2 = sr1 + PE_TY * RW;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * PE_TX, y0 = blockIdx.y * PE_TY, b = blockIdx.z;
+    const size_t plane = static_cast<size_t>(w) * h;
+    const float* Ib = I + b * plane;
+    for (int i = tid; i < RH * RW; i += PE_THREADS) {
+        int yy = i / RW, xx = i - yy * RW;
+        int gx = min(max(x0 - n + xx, 0), w - 1);
+        int gy = min(max(y0 - n + yy, 0), h - 1);
+        sI[i] = Ib[static_cast<size_t>(gy) * w + gx];
+    }
+    __syncthreads();
+    // vertical pass (rows replicate: the clamp above already did it)
+    for (int i = tid; i < PE_TY * RW; i += PE_THREADS) {
+        int ty = i / RW, xx = i - ty * RW;
+        const float* c = sI + (ty + n) * RW + xx;
+        float r0 = c[0] * pc.g[0], r1 = 0.f, r2 = 0.f;
+        for (int k = 1; k <= n; ++k) {
+            float s0 = c[-k * RW], s1 = c[k * RW];
+            float p = s0 + s1;
+            r0 = fmaf(pc.g[k], p, r0);
+            r1 = fmaf(pc.xg[k], s1 - s0, r1);
+            r2 = fmaf(pc.xxg[k], p, r2);
+        }
+        sr0[i] = r0;
+        sr1[i] = r1;
+        sr2[i] = r2;
+    }
+    __syncthreads();
+    // horizontal pass
+    float* Rb = R + static_cast<size_t>(b) * 5 * plane;
+    for (int i = tid; i < PE_TX * PE_TY; i += PE_THREADS) {
+        int ty = i / PE_TX, tx = i - ty * PE_TX;
+        int gx = x0 + tx, gy = y0 + ty;
+        if (gx >= w || gy >= h) continue;
+        const float* p0 = sr0 + ty * RW + tx + n;
+        const float* p1 = sr1 + ty * RW + tx + n;
+        const float* p2 = sr2 + ty * RW + tx + n;
+        float b1 = p0[0] * pc.g[0], b3 = p1[0] * pc.g[0], b5 = p2[0] * pc.g[0];
+        float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+        for (int k = 1; k <= n; ++k) {
+            float tg = p0[k] + p0[-k];
+            b1 = fmaf(tg, pc.g[k], b1);
+            b4 = fmaf(tg, pc.xxg[k], b4);
+            b2 = fmaf(p0[k] - p0[-k], pc.xg[k], b2);
+            b3 = fmaf(p1[k] + p1[-k], pc.g[k], b3);
+            b6 = fmaf(p1[k] - p1[-k], pc.xg[k], b6);
+            b5 = fmaf(p2[k] + p2[-k], pc.g[k], b5);
+        }
+        size_t o = static_cast<size_t>(gy) * w + gx;
+        Rb[o] = b3 * pc.ig11;
+        Rb[plane + o] = b2 * pc.ig11;
+        Rb[2 * plane + o] = fmaf(b1, pc.ig03, b5 * pc.ig33);
+        Rb[3 * plane + o] = fmaf(b1, pc.ig03, b4 * pc.ig33);
+        Rb[4 * plane + o] = b6 * pc.ig55;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// F3: flow initialisation of a finer layer = bilinear resize of the coarser flow * mul
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_upsample_flow(const float2* __restrict__ fin, float2* __restrict__ fout,
+                                                       int hi, int wi, int ho, int wo, double rx, double ry,
+                                                       double mul) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y, b = blockIdx.z;
+    if (x >= wo) return;
+    int sx, sy;
+    double fx, fy;
+    resize_tap(x, wi, rx, sx, fx);
+    resize_tap(y, hi, ry, sy, fy);
+    int sx1 = min(sx + 1, wi - 1), sy1 = min(sy + 1, hi - 1);
+    const float2* p = fin + static_cast<size_t>(b) * hi * wi;
+    float2 a = p[static_cast<size_t>(sy) * wi + sx], bb = p[static_cast<size_t>(sy) * wi + sx1];
+    float2 c = p[static_cast<size_t>(sy1) * wi + sx], d = p[static_cast<size_t>(sy1) * wi + sx1];
+    // horizontal pass rounded to f32, then vertical, as cv::resize does
+    float t0x = static_cast<float>((1.0 - fx) * a.x + fx * bb.x), t0y = static_cast<float>((1.0 - fx) * a.y + fx * bb.y);
+    float t1x = static_cast<float>((1.0 - fx) * c.x + fx * d.x), t1y = static_cast<float>((1.0 - fx) * c.y + fx * d.y);
+    float vx = static_cast<float>((1.0 - fy) * t0x + fy * t1x), vy = static_cast<float>((1.0 - fy) * t0y + fy * t1y);
+    float2 o;
+    o.x = static_cast<float>(static_cast<double>(vx) * mul);
+    o.y = static_cast<float>(static_cast<double>(vy) * mul);
+    fout[(static_cast<size_t>(b) * ho + y) * wo + x] = o;
+}
+
+// ------------------------------------------------------------------------------------
+// F5: updateMatrices for one pixel
+// ------------------------------------------------------------------------------------
+__constant__ float c_border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
+
+__device__ __forceinline__ void compute_M(const float* __restrict__ R0, const float* __restrict__ R1, size_t plane,
+                                          int w, int h, int x, int y, float2 f, float M[5]) {
+    const float dx = f.x, dy = f.y;
+    float fx = static_cast<float>(x) + dx, fy = static_cast<float>(y) + dy;
+    const float x1f = floorf(fx), y1f = floorf(fy);
+    fx -= x1f;
+    fy -= y1f;
+    const size_t o = static_cast<size_t>(y) * w + x;
+    const float q0 = R0[o], q1 = R0[plane + o], q2 = R0[2 * plane + o], q3 = R0[3 * plane + o],
+                q4 = R0[4 * plane + o];
+    float r2, r3, r4, r5, r6;
+    // float-domain test also rejects NaN / huge displacements
+    if (x1f >= 0.f && x1f < static_cast<float>(w - 1) && y1f >= 0.f && y1f < static_cast<float>(h - 1)) {
+        const int x1 = static_cast<int>(x1f), y1 = static_cast<int>(y1f);
+        const float a01 = fx * (1.f - fy), a11 = fx * fy;
+        const float a00 = (1.f - fx) * (1.f - fy), a10 = (1.f - fx) * fy;
+        const float* p = R1 + static_cast<size_t>(y1) * w + x1;
+        float s[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float* pc = p + c * plane;
+            s[c] = a00 * pc[0] + a01 * pc[1] + a10 * pc[w] + a11 * pc[w + 1];
+        }
+        r2 = s[0];
+        r3 = s[1];
+        r4 = (q2 + s[2]) * 0.5f;
+        r5 = (q3 + s[3]) * 0.5f;
+        r6 = (q4 + s[4]) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = q2;
+        r5 = q3;
+        r6 = q4 * 0.5f;
+    }
+    r2 = (q0 - r2) * 0.5f;
+    r3 = (q1 - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if (x < 5 || x >= w - 5 || y < 5 || y >= h - 5) {
+        float sc = (x < 5 ? c_border[x] : 1.f) * (x >= w - 5 ? c_border[w - 1 - x] : 1.f) *
+                   (y < 5 ? c_border[y] : 1.f) * (y >= h - 5 ? c_border[h - 1 - y] : 1.f);
+        r2 *= sc, r3 *= sc, r4 *= sc, r5 *= sc, r6 *= sc;
+    }
+    M[0] = r4 * r4 + r6 * r6;
+    M[1] = (r4 + r5) * r6;
+    M[2] = r5 * r5 + r6 * r6;
+    M[3] = r4 * r2 + r6 * r3;
+    M[4] = r6 * r2 + r5 * r3;
+}
+
+__global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict__ R0, const float* __restrict__ R1,
+                                                         const float2* __restrict__ flow, float* __restrict__ Mout,
+                                                         int w, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y, b = blockIdx.z;
+    if (x >= w) return;
+    const size_t plane = static_cast<size_t>(w) * h;
+    float M[5];
+    compute_M(R0 + b * 5 * plane, R1 + b * 5 * plane, plane, w, h, x, y, flow[b * plane + static_cast<size_t>(y) * w + x],
+              M);
+    float* o = Mout + b * 5 * plane + static_cast<size_t>(y) * w + x;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) o[c * plane] = M[c];
+}
+
+// ------------------------------------------------------------------------------------
+// F5 + F6 fused: one flow iteration.  A CTA owns a FI_TX x FI_TY tile of output pixels,
+// builds M for the tile plus an m-pixel halo in shared memory (FUSED: straight from
+// R0 / R1 / flow; otherwise from a precomputed M field), box-sums it separably with
+// direct (non-running) sums and solves the 2x2 system per pixel.
+// ------------------------------------------------------------------------------------
+constexpr int FI_TX = 32, FI_TY = 32, FI_THREADS = 256;
+
+__device__ __forceinline__ float2 solve_flow(const float g[5]) {
+    // g = blurred (g11, g12, g22, h1, h2)
+    float idet = 1.f / (g[0] * g[2] - g[1] * g[1] + 1e-3f);
+    float2 o;
+    o.x = (g[0] * g[4] - g[1] * g[3]) * idet;
+    o.y = (g[2] * g[3] - g[1] * g[4]) * idet;
+    return o;
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(FI_THREADS) k_flow_iter(const float* __restrict__ R0, const float* __restrict__ R1,
+                                                          const float2* __restrict__ flow_in,
+                                                          const float* __restrict__ Min, float2* __restrict__ flow_out,
+                                                          int w, int h, int m, float norm) {
+    extern __shared__ float smem[];
+    const int RW = FI_TX + 2 * m, RH = FI_TY + 2 * m;
+    const int SW = RW | 1;  // odd row stride
+    float* sM = smem;                       // [5][RH][SW]
+    float* sV = sM + 5 * RH * SW;           // [5][FI_TY][SW]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * FI_TX, y0 = blockIdx.y * FI_TY, b = blockIdx.z;
+    const size_t plane = static_cast<size_t>(w) * h;
+    const float* R0b = R0 + static_cast<size_t>(b) * 5 * plane;
+    const float* R1b = R1 + static_cast<size_t>(b) * 5 * plane;
+    const float* Mb = Min + static_cast<size_t>(b) * 5 * plane;
+    const float2* fb = flow_in + static_cast<size_t>(b) * plane;
+    // phase 1: M over the tile + halo (replicate border = clamp the coordinates)
+    for (int i = tid; i < RH * RW; i += FI_THREADS) {
+        int yy = i / RW, xx = i - yy * RW;
+        int gx = min(max(x0 - m + xx, 0), w - 1);
+        int gy = min(max(y0 - m + yy, 0), h - 1);
+        float M[5];
+        if (FUSED) {
+            compute_M(R0b, R1b, plane, w, h, gx, gy, fb[static_cast<size_t>(gy) * w + gx], M);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) M[c] = Mb[c * plane + static_cast<size_t>(gy) * w + gx];
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) sM[(c * RH + yy) * SW + xx] = M[c];
+    }
+    __syncthreads();
+    // phase 2: vertical window sums
+    const int win = 2 * m + 1;
+    for (int i = tid; i < 5 * FI_TY * RW; i += FI_THREADS) {
+        int xx = i % RW;
+        int t = i / RW;
+        int y = t % FI_TY, c = t / FI_TY;
+        const float* col = sM + (c * RH + y) * SW + xx;
+        float s = 0.f;
+        for (int d = 0; d < win; ++d) s += col[d * SW];
+        sV[(c * FI_TY + y) * SW + xx] = s;
+    }
+    __syncthreads();
+    // phase 3: horizontal window sums + solve
+    float2* fo = flow_out + static_cast<size_t>(b) * plane;
+    for (int i = tid; i < FI_TX * FI_TY; i += FI_THREADS) {
+        int y = i / FI_TX, x = i - y * FI_TX;
+        int gx = x0 + x, gy = y0 + y;
+        if (gx >= w || gy >= h) continue;
+        float g[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float* row = sV + (c * FI_TY + y) * SW + x;
+            float s = 0.f;
+            for (int d = 0; d < win; ++d) s += row[d];
+            g[c] = s * norm;
+        }
+        fo[static_cast<size_t>(gy) * w + gx] = solve_flow(g);
+    }
+}
+
+size_t flow_iter_smem(int m) {
+    int RW = FI_TX + 2 * m, RH = FI_TY + 2 * m, SW = RW | 1;
+    return static_cast<size_t>(5) * (RH + FI_TY) * SW * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------
+int launch_pyr(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, const FbLayer& L, const float* d_kern,
+               float* T, float* out) {
+    dim3 g1(ceil_div(L.w, 128), H, B);
+    {
+        LaunchScope ls(h, DATMO_TAG_PYRAMID);
+        if (dtype == DATMO_U8)
+            k_pyr_h<uint8_t><<<g1, 128, 0, h->stream>>>(static_cast<const uint8_t*>(img), T, H, W, L.w, d_kern,
+                                                        L.ksize, static_cast<double>(W) / L.w);
+        else
+            k_pyr_h<float><<<g1, 128, 0, h->stream>>>(static_cast<const float*>(img), T, H, W, L.w, d_kern, L.ksize,
+                                                      static_cast<double>(W) / L.w);
+    }
+    DATMO_POST_LAUNCH(h);
+    dim3 g2(ceil_div(L.w, 128), L.h, B);
+    {
+        LaunchScope ls(h, DATMO_TAG_PYRAMID);
+        k_pyr_v<<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, d_kern, L.ksize, static_cast<double>(H) / L.h);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+int launch_polyexp(datmo_ctx* h, const float* I, float* R, int w, int hh, int B, const PolyCoef& pc) {
+    int RW = PE_TX + 2 * pc.n, RH = PE_TY + 2 * pc.n;
+    size_t smem = static_cast<size_t>(RH * RW + 3 * PE_TY * RW) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(smem)));
+        configured = smem;
+    }
+    dim3 g(ceil_div(w, PE_TX), ceil_div(hh, PE_TY), B);
+    {
+        LaunchScope ls(h, DATMO_TAG_POLYEXP);
+        k_polyexp<<<g, PE_THREADS, smem, h->stream>>>(I, R, w, hh, pc);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+template <bool FUSED>
+int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, const float* Min,
+                     float* flow_out, int w, int hh, int B, int winsize) {
+    int m = winsize / 2;
+    size_t smem = flow_iter_smem(m);
+    DATMO_REQUIRE(h, smem <= 227 * 1024, "winsize too large for the flow-iteration tile");
+    static size_t configured = 0;
+    if (smem > configured) {
+        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(smem)));
+        configured = smem;
+    }
+    dim3 g(ceil_div(w, FI_TX), ceil_div(hh, FI_TY), B);
+    float norm = static_cast<float>(1.0 / (static_cast<double>(winsize) * winsize));
+    {
+        LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
+        k_flow_iter<FUSED><<<g, FI_THREADS, smem, h->stream>>>(R0, R1, reinterpret_cast<const float2*>(flow_in), Min,
+                                                               reinterpret_cast<float2*>(flow_out), w, hh, m, norm);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+int launch_update_matrices(datmo_ctx* h, const float* R0, const float* R1, const float* flow, float* M, int w,
+                           int hh, int B) {
+    dim3 g(ceil_div(w, 256), hh, B);
+    {
+        LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
+        k_update_matrices<<<g, 256, 0, h->stream>>>(R0, R1, reinterpret_cast<const float2*>(flow), M, w, hh);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+int launch_upsample(datmo_ctx* h, const float* fin, int hi, int wi, float* fout, int ho, int wo, int B, double mul) {
+    dim3 g(ceil_div(wo, 128), ho, B);
+    {
+        LaunchScope ls(h, DATMO_TAG_FLOW_INIT);
+        k_upsample_flow<<<g, 128, 0, h->stream>>>(reinterpret_cast<const float2*>(fin), reinterpret_cast<float2*>(fout),
+                                                  hi, wi, ho, wo, static_cast<double>(wi) / wo,
+                                                  static_cast<double>(hi) / ho, mul);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+int check_params(datmo_ctx* h, int H, int W, int B, const datmo_farneback_params* p) {
+    DATMO_REQUIRE(h, p != nullptr, "params is null");
+    DATMO_REQUIRE(h, H >= 2 && W >= 2 && B >= 1, "need H, W >= 2 and batch >= 1");
+    DATMO_REQUIRE(h, H <= 65535 && B <= 65535, "H and batch must fit a CUDA grid dimension");
+    DATMO_REQUIRE(h, p->flags == 0, "only flags = 0 is on the reference path (main.py:139)");
+    DATMO_REQUIRE(h, p->pyr_scale > 0 && p->pyr_scale < 1, "pyr_scale must be in (0, 1)");
+    DATMO_REQUIRE(h, p->levels >= 1 && p->winsize >= 1 && p->iterations >= 1, "levels, winsize, iterations >= 1");
+    DATMO_REQUIRE(h, p->poly_n >= 1 && p->poly_n <= POLY_MAX_N, "poly_n out of range");
+    DATMO_REQUIRE(h, flow_iter_smem(p->winsize / 2) <= 227 * 1024, "winsize too large");
+    return DATMO_OK;
+}
+
+struct FbWorkspace {
+    float* kern;   // gaussian taps of every layer, concatenated
+    float* T;      // [B][H][wmax], reused for prev then next
+    float* I;      // [2][B][h][w]
+    float* R;      // [2][B][5][h][w]
+    float* flowA;  // [B][h][w][2]
+    float* flowB;
+    float* M;      // [B][5][h][w] (unfused variant only)
+};
+
+size_t fb_carve(Bump& bump, FbWorkspace& ws, int H, int W, int B, int n_kern, bool need_M) {
+    size_t N0 = static_cast<size_t>(H) * W;
+    ws.kern = bump.take<float>(n_kern);
+    ws.T = bump.take<float>(B * N0);
+    ws.I = bump.take<float>(2 * B * N0);
+    ws.R = bump.take<float>(2 * B * 5 * N0);
+    ws.flowA = bump.take<float>(2 * B * N0);
+    ws.flowB = bump.take<float>(2 * B * N0);
+    ws.M = need_M ? bump.take<float>(5 * B * N0) : nullptr;
+    return bump.off;
+}
+
+int fb_run_chunk(datmo_ctx* h, const void* prev, const void* next, int dtype, int H, int W, int B,
+                 const datmo_farneback_params& p, const std::vector<FbLayer>& layers, const PolyCoef& pc,
+                 const FbWorkspace& ws, const std::vector<int>& kern_off, float* flow_out) {
+    float* cur = nullptr;  // flow of the layer just finished
+    int cur_w = 0, cur_h = 0;
+    const bool fused = p.variant != 1;
+    for (size_t li = 0; li < layers.size(); ++li) {
+        const FbLayer& L = layers[li];
+        const size_t n = static_cast<size_t>(L.w) * L.h;
+        const bool last_layer = li + 1 == layers.size();
+        float* I0 = ws.I;
+        float* I1 = ws.I + B * n;
+        float* R0 = ws.R;
+        float* R1 = ws.R + B * 5 * n;
+        DATMO_TRY(launch_pyr(h, prev, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I0));
+        DATMO_TRY(launch_pyr(h, next, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I1));
+        DATMO_TRY(launch_polyexp(h, ws.I, ws.R, L.w, L.h, 2 * B, pc));
+        float* fin;
+        float* fout;
+        if (cur == nullptr) {
+            fin = ws.flowA;
+            fout = ws.flowB;
+            DATMO_CHECK_CUDA(h, cudaMemsetAsync(fin, 0, B * n * 2 * sizeof(float), h->stream));
+        } else {
+            fin = cur == ws.flowA ? ws.flowB : ws.flowA;
+            fout = cur;
+            DATMO_TRY(launch_upsample(h, cur, cur_h, cur_w, fin, L.h, L.w, B, 1.0 / p.pyr_scale));
+        }
+        for (int it = 0; it < p.iterations; ++it) {
+            float* dst = (last_layer && it == p.iterations - 1) ? flow_out : fout;
+            if (fused) {
+                DATMO_TRY(launch_flow_iter<true>(h, R0, R1, fin, nullptr, dst, L.w, L.h, B, p.winsize));
+            } else {
+                DATMO_TRY(launch_update_matrices(h, R0, R1, fin, ws.M, L.w, L.h, B));
+                DATMO_TRY(launch_flow_iter<false>(h, R0, R1, fin, ws.M, dst, L.w, L.h, B, p.winsize));
+            }
+            std::swap(fin, fout);
+        }
+        cur = fin;  // after the swap, fin is what was just written
+        cur_w = L.w;
+        cur_h = L.h;
+    }
+    return DATMO_OK;
+}
+
+size_t ws_budget_bytes() {
+    const char* e = getenv("DATMO_WS_BUDGET_MB");
+    size_t mb = e ? strtoull(e, nullptr, 10) : 8192;
+    if (mb < 64) mb = 64;
+    return mb << 20;
+}
+
+int fb_run(datmo_ctx* h, const void* prev, const void* next, int dtype, int H, int W, int batch,
+           const datmo_farneback_params* p, float* flow) {
+    DATMO_TRY(check_params(h, H, W, batch, p));
+    DATMO_REQUIRE(h, prev && next && flow, "null image / flow pointer");
+    DATMO_REQUIRE(h, dtype == DATMO_U8 || dtype == DATMO_F32, "dtype must be DATMO_U8 or DATMO_F32");
+    std::vector<FbLayer> layers = fb_plan(H, W, p->pyr_scale, p->levels);
+    PolyCoef pc;
+    DATMO_REQUIRE(h, poly_setup(p->poly_n, p->poly_sigma, pc), "polynomial expansion setup failed");
+    std::vector<float> kern_all;
+    std::vector<int> kern_off;
+    for (auto& L : layers) {
+        DATMO_REQUIRE(h, L.ksize / 2 < std::min(H, W), "image too small for the pyramid smoothing kernel");
+        kern_off.push_back(static_cast<int>(kern_all.size()));
+        auto k = gaussian_kernel(L.ksize, L.sigma);
+        kern_all.insert(kern_all.end(), k.begin(), k.end());
+    }
+    const bool need_M = p->variant == 1;
+    // chunk the batch so the workspace stays inside the budget
+    FbWorkspace ws;
+    size_t per_pair;
+    {
+        Bump dry(nullptr);
+        per_pair = fb_carve(dry, ws, H, W, 1, static_cast<int>(kern_all.size()), need_M);
+    }
+    int chunk = static_cast<int>(std::max<size_t>(1, std::min<size_t>(batch, ws_budget_bytes() / per_pair)));
+    chunk = std::min(chunk, 32767);  // polyexp runs 2 * chunk images in grid.z
+    size_t total;
+    {
+        Bump dry(nullptr);
+        total = fb_carve(dry, ws, H, W, chunk, static_cast<int>(kern_all.size()), need_M);
+    }
+    DATMO_TRY(datmo_ws_reserve(h, total));
+    Bump bump(h->ws);
+    fb_carve(bump, ws, H, W, chunk, static_cast<int>(kern_all.size()), need_M);
+    // taps go through the pinned staging area so the copy is truly asynchronous
+    DATMO_TRY(datmo_pinned_reserve(h, kern_all.size() * sizeof(float)));
+    DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));  // previous call may still read the staging area
+    memcpy(h->pinned, kern_all.data(), kern_all.size() * sizeof(float));
+    DATMO_CHECK_CUDA(h, cudaMemcpyAsync(ws.kern, h->pinned, kern_all.size() * sizeof(float), cudaMemcpyHostToDevice,
+                                        h->stream));
+    const size_t N0 = static_cast<size_t>(H) * W;
+    const size_t esz = dtype == DATMO_U8 ? 1 : 4;
+    for (int b0 = 0; b0 < batch; b0 += chunk) {
+        int B = std::min(chunk, batch - b0);
+        DATMO_TRY(fb_run_chunk(h, static_cast<const char*>(prev) + b0 * N0 * esz,
+                               static_cast<const char*>(next) + b0 * N0 * esz, dtype, H, W, B, *p, layers, pc, ws,
+                               kern_off, flow + b0 * N0 * 2));
+    }
+    return DATMO_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+void datmo_farneback_default_params(datmo_farneback_params* p) {
+    if (!p) return;
+    // Optical_flow/main.py:132-140
+    p->pyr_scale = 0.3;
+    p->levels = 5;
+    p->winsize = 15;
+    p->iterations = 5;
+    p->poly_n = 5;
+    p->poly_sigma = 5.0;
+    p->flags = 0;
+    p->variant = 0;
+}
+
+int datmo_farneback_layers(int H, int W, const datmo_farneback_params* p, int max_layers, int* w, int* hh) {
+    if (!p || H < 1 || W < 1) return DATMO_E_INVALID;
+    auto layers = fb_plan(H, W, p->pyr_scale, p->levels);
+    for (size_t i = 0; i < layers.size() && static_cast<int>(i) < max_layers; ++i) {
+        if (w) w[i] = layers[i].w;
+        if (hh) hh[i] = layers[i].h;
+    }
+    return static_cast<int>(layers.size());
+}
+
+int datmo_farneback_dev(datmo_handle_t h, const void* prev, const void* next, int dtype, int H, int W, int batch,
+                        const datmo_farneback_params* p, float* flow) {
+    DATMO_ENTER(h);
+    return fb_run(h, prev, next, dtype, H, W, batch, p, flow);
+}
+
+int datmo_farneback_host(datmo_handle_t h, const void* prev, const void* next, int dtype, int H, int W, int batch,
+                         const datmo_farneback_params* p, float* flow) {
+    DATMO_ENTER(h);
+    DATMO_TRY(check_params(h, H, W, batch, p));
+    DATMO_REQUIRE(h, prev && next && flow, "null image / flow pointer");
+    DATMO_REQUIRE(h, dtype == DATMO_U8 || dtype == DATMO_F32, "dtype must be DATMO_U8 or DATMO_F32");
+    const size_t N0 = static_cast<size_t>(H) * W;
+    const size_t esz = dtype == DATMO_U8 ? 1 : 4;
+    const size_t in_bytes = batch * N0 * esz, out_bytes = batch * N0 * 2 * sizeof(float);
+    char* d_io = nullptr;
+    DATMO_CHECK_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&d_io), 2 * in_bytes + out_bytes + 1024));
+    char* d_prev = d_io;
+    char* d_next = d_io + ((in_bytes + 255) & ~size_t(255));
+    float* d_flow = reinterpret_cast<float*>(d_next + ((in_bytes + 255) & ~size_t(255)));
+    int st = DATMO_OK;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_prev, prev, in_bytes, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_next, next, in_bytes, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) {
+        h->err = cudaGetErrorString(e);
+        st = DATMO_E_CUDA;
+    }
+    if (st == DATMO_OK) st = fb_run(h, d_prev, d_next, dtype, H, W, batch, p, d_flow);
+    if (st == DATMO_OK &&
+        (e = cudaMemcpyAsync(flow, d_flow, out_bytes, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) {
+        h->err = cudaGetErrorString(e);
+        st = DATMO_E_CUDA;
+    }
+    e = cudaStreamSynchronize(h->stream);
+    if (st == DATMO_OK && e != cudaSuccess) {
+        h->err = cudaGetErrorString(e);
+        st = DATMO_E_CUDA;
+    }
+    cudaFree(d_io);
+    return st;
+}
+
+int datmo_fb_pyramid_image_dev(datmo_handle_t h, const void* img, int dtype, int H, int W, int batch, int ksize,
+                               double sigma, int h_out, int w_out, float* out) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, img && out && H >= 1 && W >= 1 && batch >= 1 && h_out >= 1 && w_out >= 1, "bad arguments");
+    DATMO_REQUIRE(h, ksize >= 1 && (ksize & 1) && ksize / 2 < std::min(H, W), "bad ksize");
+    auto k = gaussian_kernel(ksize, sigma);
+    Bump dry(nullptr);
+    dry.take<float>(ksize);
+    dry.take<float>(static_cast<size_t>(batch) * H * w_out);
+    DATMO_TRY(datmo_ws_reserve(h, dry.off));
+    Bump bump(h->ws);
+    float* d_k = bump.take<float>(ksize);
+    float* T = bump.take<float>(static_cast<size_t>(batch) * H * w_out);
+    DATMO_CHECK_CUDA(h, cudaMemcpyAsync(d_k, k.data(), ksize * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));  // k is a stack-lifetime vector
+    FbLayer L{0, 1.0, sigma, ksize, w_out, h_out};
+    return launch_pyr(h, img, dtype, H, W, batch, L, d_k, T, out);
+}
+
+int datmo_fb_polyexp_dev(datmo_handle_t h, const float* img, int hh, int ww, int batch, int poly_n, double poly_sigma,
+                         float* R) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, img && R && hh >= 1 && ww >= 1 && batch >= 1, "bad arguments");
+    PolyCoef pc;
+    DATMO_REQUIRE(h, poly_setup(poly_n, poly_sigma, pc), "polynomial expansion setup failed");
+    return launch_polyexp(h, img, R, ww, hh, batch, pc);
+}
+
+int datmo_fb_update_matrices_dev(datmo_handle_t h, const float* R0, const float* R1, const float* flow, int hh, int ww,
+                                 int batch, float* M) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, R0 && R1 && flow && M && hh >= 1 && ww >= 1 && batch >= 1, "bad arguments");
+    return launch_update_matrices(h, R0, R1, flow, M, ww, hh, batch);
+}
+
+int datmo_fb_blur_solve_dev(datmo_handle_t h, const float* M, int hh, int ww, int batch, int winsize, float* flow) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, M && flow && hh >= 1 && ww >= 1 && batch >= 1 && winsize >= 1, "bad arguments");
+    return launch_flow_iter<false>(h, M, M, flow, M, flow, ww, hh, batch, winsize);
+}
+
+int datmo_fb_flow_iter_dev(datmo_handle_t h, const float* R0, const float* R1, const float* flow_in, int hh, int ww,
+                           int batch, int winsize, float* flow_out) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, R0 && R1 && flow_in && flow_out && flow_in != flow_out, "bad arguments");
+    DATMO_REQUIRE(h, hh >= 1 && ww >= 1 && batch >= 1 && winsize >= 1, "bad arguments");
+    return launch_flow_iter<true>(h, R0, R1, flow_in, nullptr, flow_out, ww, hh, batch, winsize);
+}
+
+int datmo_fb_upsample_flow_dev(datmo_handle_t h, const float* flow_in, int h_in, int w_in, int batch, int h_out,
+                               int w_out, double mul, float* flow_out) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, flow_in && flow_out && h_in >= 1 && w_in >= 1 && h_out >= 1 && w_out >= 1 && batch >= 1,
+                  "bad arguments");
+    return launch_upsample(h, flow_in, h_in, w_in, flow_out, h_out, w_out, batch, mul);
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+// RANSAC ground-plane segmentation, sm_100a.
+//
+// Replaces flipped_pcd.segment_plane(distance_threshold=0.5, ransac_n=5,
+// num_iterations=5000) at Optical_flow/main.py:73 (Open3D; absent from this image, so
+// the algorithm is the published one as restated in oracle/ransac_np.py — PARITY
+// UNPINNED against the real library).
+//
+// All hypotheses are independent, so they are scored as one batch instead of Open3D's
+// iteration loop:
+//   k_ransac_hyp    one thread per hypothesis: counter-hash sample indices, plane through
+//                   the samples (3 points: triangle normal; more: centroid + covariance
+//                   cofactors), fp64
+//   k_ransac_score  a CTA holds a tile of points in shared memory and 256 hypotheses in
+//                   registers, one per thread; every thread walks the tile (broadcast
+//                   shared-memory reads) testing |a x + b y + c z + d| < thr in fp64 and keeps
+//                   its own inlier count / error sum: no atomics, no cross-thread traffic
+//                   in the hot loop; per-tile partials are reduced in tile order
+//                   (deterministic)
+//   k_ransac_best   warp-shuffle arg-max over (count desc, rmse asc, index asc)
+//   k_ransac_mask   inlier mask of the winner + moments for the refit
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int RS_ATTEMPTS = 16;
+constexpr int RS_MAX_N = 8;        // samples per hypothesis
+constexpr int RS_TILE = 2048;      // points per CTA tile
+constexpr int RS_THREADS = 256;    // hypotheses per CTA
+
+__device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t ctr) {
+    uint64_t z = seed + (ctr + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ void load_point(const void* pts, int64_t i, int flip_x, double& x, double& y, double& z) {
+    if (LAYOUT == DATMO_PTS_F64_XYZ) {
+        const double* p = static_cast<const double*>(pts) + 3 * i;
+        x = p[0], y = p[1], z = p[2];
+    } else {
+        const float4 p = static_cast<const float4*>(pts)[i];
+        x = p.x, y = p.y, z = p.z;
+    }
+    if (flip_x) x = -x;
+}
+
+// GetPlaneFromPoints on moments: centroid c, deviations' second moments
+__device__ __forceinline__ void plane_from_moments(double cx, double cy, double cz, double xx, double xy, double xz,
+                                                   double yy, double yz, double zz, double out[4]) {
+    const double det_x = yy * zz - yz * yz;
+    const double det_y = xx * zz - xz * xz;
+    const double det_z = xx * yy - xy * xy;
+    double a, b, c;
+    if (det_x > det_y && det_x > det_z) {
+        a = det_x, b = xz * yz - xy * zz, c = xy * yz - xz * yy;
+    } else if (det_y > det_z) {
+        a = xz * yz - xy * zz, b = det_y, c = xy * xz - yz * xx;
+    } else {
+        a = xy * yz - xz * yy, b = xy * xz - yz * xx, c = det_z;
+    }
+    const double norm = sqrt(a * a + b * b + c * c);
+    if (!(norm > 0.0) || !isfinite(norm)) {
+        out[0] = out[1] = out[2] = out[3] = 0.0;
+        return;
+    }
+    a /= norm, b /= norm, c /= norm;
+    out[0] = a, out[1] = b, out[2] = c;
+    out[3] = -(a * cx + b * cy + c * cz);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(128) k_ransac_hyp(const void* __restrict__ pts, int64_t n, int flip_x, int ransac_n,
+                                                    int iters, uint64_t seed, double* __restrict__ planes) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= iters) return;
+    int64_t idx[RS_MAX_N];
+    int filled = 0;
+    for (int t = 0; t < RS_ATTEMPTS && filled < ransac_n; ++t) {
+        int64_t cand = static_cast<int64_t>(mix64(seed, static_cast<uint64_t>(it) * RS_ATTEMPTS + t) %
+                                            static_cast<uint64_t>(n));
+        bool dup = false;
+        for (int j = 0; j < filled; ++j) dup |= idx[j] == cand;
+        if (!dup) idx[filled++] = cand;
+    }
+    double out[4] = {0, 0, 0, 0};
+    if (filled >= ransac_n) {
+        double px[RS_MAX_N], py[RS_MAX_N], pz[RS_MAX_N];
+        for (int j = 0; j < ransac_n; ++j) load_point<LAYOUT>(pts, idx[j], flip_x, px[j], py[j], pz[j]);
+        if (ransac_n == 3) {
+            const double e0x = px[1] - px[0], e0y = py[1] - py[0], e0z = pz[1] - pz[0];
+            const double e1x = px[2] - px[0], e1y = py[2] - py[0], e1z = pz[2] - pz[0];
+            double a = e0y * e1z - e0z * e1y, b = e0z * e1x - e0x * e1z, c = e0x * e1y - e0y * e1x;
+            const double norm = sqrt(a * a + b * b + c * c);
+            if (norm > 0.0 && isfinite(norm)) {
+                a /= norm, b /= norm, c /= norm;
+                out[0] = a, out[1] = b, out[2] = c;
+                out[3] = -(a * px[0] + b * py[0] + c * pz[0]);
+            }
+        } else {
+            double cx = 0, cy = 0, cz = 0;
+            for (int j = 0; j < ransac_n; ++j) cx += px[j], cy += py[j], cz += pz[j];
+            cx /= ransac_n, cy /= ransac_n, cz /= ransac_n;
+            double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
+            for (int j = 0; j < ransac_n; ++j) {
+                const double rx = px[j] - cx, ry = py[j] - cy, rz = pz[j] - cz;
+                xx += rx * rx, xy += rx * ry, xz += rx * rz, yy += ry * ry, yz += ry * rz, zz += rz * rz;
+            }
+            plane_from_moments(cx, cy, cz, xx, xy, xz, yy, yz, zz, out);
+        }
+    }
+    double* o = planes + 4 * static_cast<size_t>(it);
+    o[0] = out[0], o[1] = out[1], o[2] = out[2], o[3] = out[3];
+}
+
+__device__ __forceinline__ double plane_dist(double a, double b, double c, double d, double x, double y, double z) {
+    // |((a*x + b*y) + c*z) + d|, every operation rounded (matches the oracle bit for bit)
+    return fabs(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a, x), __dmul_rn(b, y)), __dmul_rn(c, z)), d));
+}
+
+// grid: (point tiles, hypothesis groups).  part_*: [n_tiles][iters]
+template <int LAYOUT>
+__global__ void __launch_bounds__(RS_THREADS) k_ransac_score(const void* __restrict__ pts, int64_t n, int flip_x,
+                                                             const double* __restrict__ planes, int iters, double thr,
+                                                             int32_t* __restrict__ part_cnt,
+                                                             double* __restrict__ part_err) {
+    __shared__ double sx[RS_TILE], sy[RS_TILE], sz[RS_TILE];
+    const int64_t p0 = static_cast<int64_t>(blockIdx.x) * RS_TILE;
+    const int np = static_cast<int>(min(static_cast<int64_t>(RS_TILE), n - p0));
+    for (int i = threadIdx.x; i < np; i += RS_THREADS) load_point<LAYOUT>(pts, p0 + i, flip_x, sx[i], sy[i], sz[i]);
+    __syncthreads();
+    const int hyp = blockIdx.y * RS_THREADS + threadIdx.x;
+    if (hyp >= iters) return;
+    const double a = planes[4 * hyp], b = planes[4 * hyp + 1], c = planes[4 * hyp + 2], d = planes[4 * hyp + 3];
+    int cnt = 0;
+    double err = 0.0;
+    if (a != 0.0 || b != 0.0 || c != 0.0 || d != 0.0) {
+#pragma unroll 4
+        for (int i = 0; i < np; ++i) {
+            const double dist = plane_dist(a, b, c, d, sx[i], sy[i], sz[i]);
+            if (dist < thr) {
+                ++cnt;
+                err += dist;
+            }
+        }
+    }
+    part_cnt[static_cast<size_t>(blockIdx.x) * iters + hyp] = cnt;
+    part_err[static_cast<size_t>(blockIdx.x) * iters + hyp] = err;
+}
+
+__global__ void __launch_bounds__(256) k_ransac_reduce(const int32_t* __restrict__ part_cnt,
+                                                       const double* __restrict__ part_err, int n_tiles, int iters,
+                                                       int32_t* __restrict__ cnt, double* __restrict__ err) {
+    const int hyp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hyp >= iters) return;
+    int c = 0;
+    double e = 0.0;
+    for (int t = 0; t < n_tiles; ++t) {
+        c += part_cnt[static_cast<size_t>(t) * iters + hyp];
+        e += part_err[static_cast<size_t>(t) * iters + hyp];
+    }
+    cnt[hyp] = c;
+    err[hyp] = e;
+}
+
+struct Cand {
+    int cnt;
+    double rmse;
+    int idx;
+};
+__device__ __forceinline__ bool better(const Cand& a, const Cand& b) {
+    // is a better than b?
+    if (a.cnt != b.cnt) return a.cnt > b.cnt;
+    if (a.rmse != b.rmse) return a.rmse < b.rmse;
+    return a.idx < b.idx;
+}
+
+// one CTA; best: {index, count}; plane: winner
+__global__ void __launch_bounds__(1024) k_ransac_best(const int32_t* __restrict__ cnt, const double* __restrict__ err,
+                                                      const double* __restrict__ planes, int iters,
+                                                      int32_t* __restrict__ best, double* __restrict__ plane) {
+    Cand me{0, 1e300, 0x7fffffff};
+    for (int i = threadIdx.x; i < iters; i += blockDim.x) {
+        const int c = cnt[i];
+        if (c <= 0) continue;
+        Cand o{c, err[i] / sqrt(static_cast<double>(c)), i};
+        if (better(o, me)) me = o;
+    }
+    __shared__ Cand s_c[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Cand t;
+        t.cnt = __shfl_down_sync(0xffffffffu, me.cnt, o);
+        t.rmse = __shfl_down_sync(0xffffffffu, me.rmse, o);
+        t.idx = __shfl_down_sync(0xffffffffu, me.idx, o);
+        if (better(t, me)) me = t;
+    }
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = me;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Cand b = s_c[0];
+        for (int i = 1; i < static_cast<int>(blockDim.x >> 5); ++i)
+            if (better(s_c[i], b)) b = s_c[i];
+        const bool ok = b.cnt > 0;
+        best[0] = ok ? b.idx : -1;
+        best[1] = ok ? b.cnt : 0;
+        for (int j = 0; j < 4; ++j) plane[j] = ok ? planes[4 * static_cast<size_t>(b.idx) + j] : 0.0;
+    }
+}
+
+// inlier mask of the winner + one-pass moments (n, sum p, sum p p^T) for the refit
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) k_ransac_mask(const void* __restrict__ pts, int64_t n, int flip_x,
+                                                     const double* __restrict__ plane, double thr,
+                                                     uint8_t* __restrict__ mask, double* __restrict__ mom) {
+    const double a = plane[0], b = plane[1], c = plane[2], d = plane[3];
+    const bool have = a != 0.0 || b != 0.0 || c != 0.0 || d != 0.0;
+    double m[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double x, y, z;
+        load_point<LAYOUT>(pts, i, flip_x, x, y, z);
+        const bool in = have && plane_dist(a, b, c, d, x, y, z) < thr;
+        mask[i] = in;
+        if (in) {
+            m[0] += 1.0, m[1] += x, m[2] += y, m[3] += z;
+            m[4] += x * x, m[5] += x * y, m[6] += x * z, m[7] += y * y, m[8] += y * z, m[9] += z * z;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m[j] += __shfl_down_sync(0xffffffffu, m[j], o);
+    }
+    if ((threadIdx.x & 31) == 0 && m[0] > 0.0) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) atomicAdd(mom + j, m[j]);
+    }
+}
+
+__global__ void k_ransac_refit(const double* __restrict__ mom, const double* __restrict__ plane,
+                               double* __restrict__ refit) {
+    const double n = mom[0];
+    if (n < 3.0) {
+        for (int j = 0; j < 4; ++j) refit[j] = plane[j];
+        return;
+    }
+    const double cx = mom[1] / n, cy = mom[2] / n, cz = mom[3] / n;
+    double out[4];
+    plane_from_moments(cx, cy, cz, mom[4] - n * cx * cx, mom[5] - n * cx * cy, mom[6] - n * cx * cz,
+                       mom[7] - n * cy * cy, mom[8] - n * cy * cz, mom[9] - n * cz * cz, out);
+    const bool zero = out[0] == 0.0 && out[1] == 0.0 && out[2] == 0.0;
+    for (int j = 0; j < 4; ++j) refit[j] = zero ? plane[j] : out[j];
+}
+
+struct RsWs {
+    double* planes;
+    int32_t* part_cnt;
+    double* part_err;
+    int32_t* cnt;
+    double* err;
+    double* mom;
+};
+
+size_t rs_carve(Bump& bump, RsWs& ws, int64_t n, int iters) {
+    const size_t n_tiles = static_cast<size_t>(ceil_div64(n, RS_TILE));
+    ws.planes = bump.take<double>(4 * static_cast<size_t>(iters));
+    ws.part_cnt = bump.take<int32_t>(n_tiles * iters);
+    ws.part_err = bump.take<double>(n_tiles * iters);
+    ws.cnt = bump.take<int32_t>(iters);
+    ws.err = bump.take<double>(iters);
+    ws.mom = bump.take<double>(16);
+    return bump.off;
+}
+
+template <int LAYOUT>
+int rs_run(datmo_ctx* h, const void* pts, int64_t n, int flip_x, double thr, int ransac_n, int iters, uint64_t seed,
+           double* plane, double* refit, uint8_t* inlier_mask, int32_t* best, double* hyp_planes, int32_t* hyp_count,
+           double* hyp_err, size_t ws_offset) {
+    RsWs ws;
+    Bump bump(h->ws + ws_offset);
+    rs_carve(bump, ws, n, iters);
+    double* planes = hyp_planes ? hyp_planes : ws.planes;
+    int32_t* cnt = hyp_count ? hyp_count : ws.cnt;
+    double* err = hyp_err ? hyp_err : ws.err;
+    const int n_tiles = static_cast<int>(ceil_div64(n, RS_TILE));
+    {
+        LaunchScope ls(h, DATMO_TAG_RANSAC);
+        k_ransac_hyp<LAYOUT><<<ceil_div(iters, 128), 128, 0, h->stream>>>(pts, n, flip_x, ransac_n, iters, seed, planes);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, DATMO_TAG_RANSAC);
+        dim3 g(n_tiles, ceil_div(iters, RS_THREADS));
+        k_ransac_score<LAYOUT><<<g, RS_THREADS, 0, h->stream>>>(pts, n, flip_x, planes, iters, thr, ws.part_cnt,
+                                                                ws.part_err);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, DATMO_TAG_RANSAC);
+        k_ransac_reduce<<<ceil_div(iters, 256), 256, 0, h->stream>>>(ws.part_cnt, ws.part_err, n_tiles, iters, cnt, err);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, DATMO_TAG_RANSAC);
+        k_ransac_best<<<1, 1024, 0, h->stream>>>(cnt, err, planes, iters, best, plane);
+    }
+    DATMO_POST_LAUNCH(h);
+    DATMO_CHECK_CUDA(h, cudaMemsetAsync(ws.mom, 0, 16 * sizeof(double), h->stream));
+    {
+        LaunchScope ls(h, DATMO_TAG_RANSAC);
+        int64_t blocks = ceil_div64(n, 256);
+        int grid = static_cast<int>(blocks > h->sm_count * 8 ? h->sm_count * 8 : blocks);
+        k_ransac_mask<LAYOUT><<<grid, 256, 0, h->stream>>>(pts, n, flip_x, plane, thr, inlier_mask, ws.mom);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, DATMO_TAG_RANSAC);
+        k_ransac_refit<<<1, 1, 0, h->stream>>>(ws.mom, plane, refit);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+}  // namespace
+
+size_t datmo_ransac_ws_bytes(int64_t n, int iters) {
+    Bump dry(nullptr);
+    RsWs ws;
+    return rs_carve(dry, ws, n, iters);
+}
+
+// shared with bev.cu's fused preprocessing; scratch lives at h->ws + ws_offset (already reserved)
+int datmo_ransac_run(datmo_ctx* h, const void* pts, int layout, int64_t n, int flip_x, double thr, int ransac_n,
+                     int iters, uint64_t seed, double* plane, double* refit, uint8_t* inlier_mask, int32_t* best,
+                     double* hyp_planes, int32_t* hyp_count, double* hyp_err, size_t ws_offset) {
+    DATMO_REQUIRE(h, pts && plane && refit && inlier_mask && best, "null pointer");
+    DATMO_REQUIRE(h, layout == DATMO_PTS_F64_XYZ || layout == DATMO_PTS_F32_XYZW, "unknown point layout");
+    DATMO_REQUIRE(h, ransac_n >= 3 && ransac_n <= RS_MAX_N, "ransac_n must be in [3, 8]");
+    DATMO_REQUIRE(h, n >= ransac_n, "There must be at least 'ransac_n' points.");
+    DATMO_REQUIRE(h, iters >= 1 && iters <= (1 << 24) && thr > 0, "bad num_iterations / distance_threshold");
+    if (layout == DATMO_PTS_F64_XYZ)
+        return rs_run<DATMO_PTS_F64_XYZ>(h, pts, n, flip_x, thr, ransac_n, iters, seed, plane, refit, inlier_mask, best,
+                                         hyp_planes, hyp_count, hyp_err, ws_offset);
+    return rs_run<DATMO_PTS_F32_XYZW>(h, pts, n, flip_x, thr, ransac_n, iters, seed, plane, refit, inlier_mask, best,
+                                      hyp_planes, hyp_count, hyp_err, ws_offset);
+}
+
+extern "C" int datmo_ransac_ground_dev(datmo_handle_t h, const void* pts, int layout, int64_t n, int flip_x,
+                                       double distance_threshold, int ransac_n, int num_iterations, uint64_t seed,
+                                       double* plane, double* refit, uint8_t* inlier_mask, int32_t* best,
+                                       double* hyp_planes, int32_t* hyp_count, double* hyp_err) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, n >= 1 && num_iterations >= 1, "empty cloud / no iterations");
+    DATMO_TRY(datmo_ws_reserve(h, datmo_ransac_ws_bytes(n, num_iterations)));
+    return datmo_ransac_run(h, pts, layout, n, flip_x, distance_threshold, ransac_n, num_iterations, seed, plane, refit,
+                            inlier_mask, best, hyp_planes, hyp_count, hyp_err, 0);
+}

@@ -1,0 +1,116 @@
+// Velocity grid, continuity mask and moving-cell filter, sm_100a.
+//
+// Replaces, in one pass over the flow field:
+//   compute_velocity_vectors tail   Optical_flow/main.py:143-164  velocity = flow * pixel size, curl
+//   continuity_mask                 Optical_flow/main.py:224-228  |div| <= a and |curl| <= a (np.gradient)
+//   inline moving-cell filter       Optical_flow/main.py:596-609  v * mask, magnitude, mag > 0.1
+// np.gradient: central difference / 2 in the interior, one-sided first order at the
+// edges, f32 in -> f32 out; the comparison against alpha happens in f32 (numpy's weak
+// python-scalar promotion); v * mask promotes to f64 and the magnitude test runs in f64.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float grad1(float lo, float c, float hi, int i, int n) {
+    // lo / hi are the samples at i-1 / i+1 (unused at the edges)
+    if (i == 0) return hi - c;
+    if (i == n - 1) return c - lo;
+    return (hi - lo) / 2.0f;
+}
+
+__global__ void __launch_bounds__(256) k_velmask(const float2* __restrict__ flow, int H, int W, float px, float py,
+                                                 float alpha, double thresh, float* __restrict__ vx_o,
+                                                 float* __restrict__ vy_o, float* __restrict__ ang_o,
+                                                 uint8_t* __restrict__ mask_o, float* __restrict__ vxf_o,
+                                                 float* __restrict__ vyf_o, uint8_t* __restrict__ valid_o,
+                                                 int32_t* __restrict__ n_valid) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    int is_valid = 0;
+    if (x < W) {
+        const size_t base = static_cast<size_t>(b) * H * W;
+        const float2* f = flow + base;
+        const size_t o = static_cast<size_t>(y) * W + x;
+        const float2 c = f[o];
+        const float2 l = f[o - (x > 0)], r = f[o + (x < W - 1)];
+        const float2 u = f[o - (y > 0 ? W : 0)], d = f[o + (y < H - 1 ? W : 0)];
+        const float vx = __fmul_rn(c.x, px), vy = __fmul_rn(c.y, py);
+        const float dvx_dx = grad1(__fmul_rn(l.x, px), vx, __fmul_rn(r.x, px), x, W);
+        const float dvy_dx = grad1(__fmul_rn(l.y, py), vy, __fmul_rn(r.y, py), x, W);
+        const float dvx_dy = grad1(__fmul_rn(u.x, px), vx, __fmul_rn(d.x, px), y, H);
+        const float dvy_dy = grad1(__fmul_rn(u.y, py), vy, __fmul_rn(d.y, py), y, H);
+        const float div = __fadd_rn(dvx_dx, dvy_dy);
+        const float curl = __fsub_rn(dvy_dx, dvx_dy);
+        const int m = (fabsf(div) <= alpha) && (fabsf(curl) <= alpha);
+        const float vxf = m ? vx : 0.f, vyf = m ? vy : 0.f;
+        const double dx = vxf, dy = vyf;
+        const double mag = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        is_valid = mag > thresh;
+        if (vx_o) vx_o[base + o] = vx;
+        if (vy_o) vy_o[base + o] = vy;
+        if (ang_o) ang_o[base + o] = curl;
+        if (mask_o) mask_o[base + o] = static_cast<uint8_t>(m);
+        if (vxf_o) vxf_o[base + o] = vxf;
+        if (vyf_o) vyf_o[base + o] = vyf;
+        if (valid_o) valid_o[base + o] = static_cast<uint8_t>(is_valid);
+    }
+    if (n_valid) {
+        // warp-shuffle reduction, then one atomic per warp
+        unsigned bal = __ballot_sync(0xffffffffu, is_valid);
+        if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_valid + b, __popc(bal));
+    }
+}
+
+// curl of the FILTERED field (main.py:604-606); f64 arithmetic on f32-representable
+// values, stored as f32 (the reference only writes it to a CSV).
+__global__ void __launch_bounds__(256) k_curl_filtered(const float* __restrict__ vxf, const float* __restrict__ vyf,
+                                                       int H, int W, float* __restrict__ ang_f) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const size_t o = static_cast<size_t>(y) * W + x;
+    const float* vx = vxf + base;
+    const float* vy = vyf + base;
+    double dvy_dx, dvx_dy;
+    if (x == 0)
+        dvy_dx = static_cast<double>(vy[o + 1]) - vy[o];
+    else if (x == W - 1)
+        dvy_dx = static_cast<double>(vy[o]) - vy[o - 1];
+    else
+        dvy_dx = (static_cast<double>(vy[o + 1]) - vy[o - 1]) / 2.0;
+    if (y == 0)
+        dvx_dy = static_cast<double>(vx[o + W]) - vx[o];
+    else if (y == H - 1)
+        dvx_dy = static_cast<double>(vx[o]) - vx[o - W];
+    else
+        dvx_dy = (static_cast<double>(vx[o + W]) - vx[o - W]) / 2.0;
+    ang_f[base + o] = static_cast<float>(dvy_dx - dvx_dy);
+}
+
+}  // namespace
+
+extern "C" int datmo_velocity_mask_dev(datmo_handle_t h, const float* flow, int H, int W, int batch, double px_x,
+                                       double px_y, double alpha_cont, double thresh, float* vx, float* vy, float* ang,
+                                       uint8_t* mask, float* vx_f, float* vy_f, float* ang_f, uint8_t* valid,
+                                       int32_t* n_valid) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, flow && H >= 2 && W >= 2 && batch >= 1, "need flow, H, W >= 2 (np.gradient) and batch >= 1");
+    DATMO_REQUIRE(h, H <= 65535 && batch <= 65535, "H and batch must fit a CUDA grid dimension");
+    DATMO_REQUIRE(h, !ang_f || (vx_f && vy_f), "ang_f needs vx_f and vy_f");
+    if (n_valid) DATMO_CHECK_CUDA(h, cudaMemsetAsync(n_valid, 0, batch * sizeof(int32_t), h->stream));
+    dim3 g(ceil_div(W, 256), H, batch);
+    {
+        LaunchScope ls(h, DATMO_TAG_VELMASK);
+        k_velmask<<<g, 256, 0, h->stream>>>(reinterpret_cast<const float2*>(flow), H, W, static_cast<float>(px_x),
+                                            static_cast<float>(px_y), static_cast<float>(alpha_cont), thresh, vx, vy,
+                                            ang, mask, vx_f, vy_f, valid, n_valid);
+    }
+    DATMO_POST_LAUNCH(h);
+    if (ang_f) {
+        LaunchScope ls(h, DATMO_TAG_VELMASK);
+        k_curl_filtered<<<g, 256, 0, h->stream>>>(vx_f, vy_f, H, W, ang_f);
+        DATMO_POST_LAUNCH(h);
+    }
+    return DATMO_OK;
+}

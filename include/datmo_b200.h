@@ -1,0 +1,207 @@
+/*
+ * datmo_b200 — C ABI of the B200-native DATMO optical-flow hot path.
+ *
+ * The reference (anvithaanchala/DATMO_using_Optical_flow) is pure Python and has
+ * no FFI layer of its own: the boundary a maintainer binds is the set of stage
+ * functions that Optical_flow/main.py:process_multiple_frames calls.  Each
+ * entry point below names the reference function (file:line) it replaces.
+ * The ctypes binding that ships with this repo is
+ * datmo_using_optical_flow_b200/_lib.py; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - every function returns an int status: 0 = ok, negative = error (see
+ *    DATMO_E_*); nothing throws, nothing aborts.  datmo_last_error() returns a
+ *    human-readable message for the last failing call on that handle.
+ *  - a handle is bound to one CUDA device and one stream; calls on one handle
+ *    must not overlap; different handles are independent (one per thread / rank).
+ *  - "_dev" entry points take DEVICE pointers, enqueue work on the handle's
+ *    stream and return without synchronising (unless stated);
+ *    "_host" entry points take HOST pointers, copy in, run, copy out and
+ *    synchronise before returning.
+ *  - there is no CPU fallback anywhere in this library.
+ *  - images are row-major (H rows, W columns), batches are contiguous [B][H][W].
+ */
+#ifndef DATMO_B200_H
+#define DATMO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DATMO_ABI_VERSION 1
+
+#define DATMO_OK 0
+#define DATMO_E_INVALID -1   /* bad argument */
+#define DATMO_E_CUDA -2      /* a CUDA call failed; see datmo_last_error */
+#define DATMO_E_CAPACITY -3  /* an output buffer was too small; counts are still written */
+#define DATMO_E_EMPTY -4     /* nothing to do (e.g. no point inside the ROI) */
+
+typedef struct datmo_ctx* datmo_handle_t;
+
+/* image element types for the Farneback inputs */
+#define DATMO_U8 0
+#define DATMO_F32 1
+/* point layouts */
+#define DATMO_PTS_F64_XYZ 0  /* double[n][3], what main.py passes around */
+#define DATMO_PTS_F32_XYZW 1 /* float[n][4], CARLA's native layout */
+
+/* ---- lifecycle ------------------------------------------------------------- */
+/* stream: a cudaStream_t to run on (borrowed), or NULL to create a private
+ * non-blocking stream. */
+int datmo_create(int device, void* stream, datmo_handle_t* out);
+int datmo_destroy(datmo_handle_t h);
+int datmo_abi_version(void);
+const char* datmo_last_error(datmo_handle_t h);
+int datmo_synchronize(datmo_handle_t h);
+/* bytes of device workspace currently held by the handle */
+size_t datmo_workspace_bytes(datmo_handle_t h);
+
+/* ---- per-kernel timing (bench.py's roofline leg) -------------------------------
+ * When enabled, the handle brackets every launch of its tagged kernels with CUDA
+ * events on its own stream.  datmo_profile_read synchronises and returns, per tag,
+ * the number of launches and the summed device time in milliseconds since the last
+ * reset.  Tags: see DATMO_TAG_*.  */
+#define DATMO_TAG_PYRAMID 0
+#define DATMO_TAG_POLYEXP 1
+#define DATMO_TAG_FLOW_INIT 2
+#define DATMO_TAG_FLOW_ITER 3   /* the fused updateMatrices + blur + solve kernel */
+#define DATMO_TAG_VELMASK 4
+#define DATMO_TAG_DBSCAN 5
+#define DATMO_TAG_BEV 6
+#define DATMO_TAG_RANSAC 7
+#define DATMO_TAG_CLUSTER 8
+#define DATMO_TAG_COUNT 9
+int datmo_profile_enable(datmo_handle_t h, int on);
+int datmo_profile_reset(datmo_handle_t h);
+int datmo_profile_read(datmo_handle_t h, int64_t launches[DATMO_TAG_COUNT], double ms[DATMO_TAG_COUNT]);
+/* total kernel launches issued by this handle since creation */
+int64_t datmo_launch_count(datmo_handle_t h);
+
+/* ---- Farneback dense optical flow ----------------------------------------------
+ * Replaces cv2.calcOpticalFlowFarneback as called by compute_velocity_vectors,
+ * Optical_flow/main.py:131-142 (parameters hard-coded at main.py:132-140:
+ * pyr_scale 0.3, levels 5, winsize 15, iterations 5, poly_n 5, poly_sigma 5,
+ * flags 0).  flags must be 0 (the only value on the reference path). */
+typedef struct datmo_farneback_params {
+    double pyr_scale;
+    int levels;
+    int winsize;
+    int iterations;
+    int poly_n;
+    double poly_sigma;
+    int flags;
+    int variant; /* 0 = default; 1 = unfused updateMatrices / blur+solve (debug / A-B) */
+} datmo_farneback_params;
+void datmo_farneback_default_params(datmo_farneback_params* p);
+/* number of pyramid layers actually processed and their sizes (coarsest first);
+ * returns the layer count, fills up to max_layers entries of w[] and h[]. */
+int datmo_farneback_layers(int H, int W, const datmo_farneback_params* p, int max_layers, int* w, int* h);
+/* prev/next: [batch][H][W] of dtype; flow: float [batch][H][W][2] (dx, dy). */
+int datmo_farneback_dev(datmo_handle_t h, const void* prev, const void* next, int dtype, int H, int W,
+                        int batch, const datmo_farneback_params* p, float* flow);
+int datmo_farneback_host(datmo_handle_t h, const void* prev, const void* next, int dtype, int H, int W,
+                         int batch, const datmo_farneback_params* p, float* flow);
+
+/* stage-level entry points (device pointers), used by the parity tests to diff
+ * each step against the oracle.  R arrays are planar float [batch][5][h][w]. */
+int datmo_fb_pyramid_image_dev(datmo_handle_t h, const void* img, int dtype, int H, int W, int batch,
+                               int ksize, double sigma, int h_out, int w_out, float* out);
+int datmo_fb_polyexp_dev(datmo_handle_t h, const float* img, int hh, int ww, int batch, int poly_n,
+                         double poly_sigma, float* R);
+int datmo_fb_update_matrices_dev(datmo_handle_t h, const float* R0, const float* R1, const float* flow,
+                                 int hh, int ww, int batch, float* M);
+int datmo_fb_blur_solve_dev(datmo_handle_t h, const float* M, int hh, int ww, int batch, int winsize,
+                            float* flow);
+int datmo_fb_flow_iter_dev(datmo_handle_t h, const float* R0, const float* R1, const float* flow_in,
+                           int hh, int ww, int batch, int winsize, float* flow_out);
+int datmo_fb_upsample_flow_dev(datmo_handle_t h, const float* flow_in, int h_in, int w_in, int batch,
+                               int h_out, int w_out, double mul, float* flow_out);
+
+/* ---- velocity grid, continuity mask, moving-cell filter ------------------------
+ * Replaces the tail of compute_velocity_vectors (main.py:143-164: velocity =
+ * flow * pixel size, curl), continuity_mask (main.py:224-228) and the inline
+ * filter of process_multiple_frames (main.py:596-609).
+ * flow: float [batch][H][W][2].  Outputs (any may be NULL), all [batch][H][W]:
+ *   vx, vy      float   velocity (m per frame; the reference ignores dt)
+ *   ang         float   curl of the unfiltered velocity (main.py:160)
+ *   mask        uint8   continuity mask 0/1
+ *   vx_f, vy_f  float   velocity * mask
+ *   ang_f       float   curl of the filtered field (main.py:604-606), as float
+ *   valid       uint8   sqrt(vx_f^2 + vy_f^2) > thresh, evaluated in fp64
+ *   n_valid     int32 [batch]  number of valid cells per frame pair */
+int datmo_velocity_mask_dev(datmo_handle_t h, const float* flow, int H, int W, int batch, double px_x,
+                            double px_y, double alpha_cont, double thresh, float* vx, float* vy,
+                            float* ang, uint8_t* mask, float* vx_f, float* vy_f, float* ang_f,
+                            uint8_t* valid, int32_t* n_valid);
+
+/* ---- DBSCAN over (row, col, vx, vy) of the valid cells --------------------------
+ * Replaces dbscan_clustering, main.py:231-259 (sklearn.cluster.DBSCAN on the
+ * row-major list of valid cells).  Labels are identical to sklearn's, including
+ * numbering.  vx_f, vy_f: float [batch][H][W]; valid: uint8 [batch][H][W].
+ * Outputs: n_valid int32[batch]; labels int32 [batch][cap]; indices int32
+ * [batch][cap][2] (row, col) in row-major order of the valid cells; n_clusters
+ * int32[batch] (may be NULL).  If any frame has more than cap valid cells the
+ * call returns DATMO_E_CAPACITY after writing n_valid (host entry point only;
+ * the device entry point truncates and the caller checks n_valid). */
+int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const float* vy_f, const uint8_t* valid,
+                          int H, int W, int batch, double eps, int min_samples, int cap,
+                          int32_t* n_valid, int32_t* labels, int32_t* indices, int32_t* n_clusters);
+
+/* ---- cluster summaries ------------------------------------------------------------
+ * Replaces extract_cluster_data, main.py:402-434.  For each frame and each label
+ * l < max_clusters writes 8 doubles: count, mean row, mean col, mean vx, mean vy,
+ * cov(row,row), cov(row,col), cov(col,col) (ddof 1, NaN when count < 2);
+ * the eigenvalues follow on the host from the 2x2 covariance.
+ * summary: double [batch][max_clusters][8]. */
+int datmo_cluster_summary_dev(datmo_handle_t h, const float* vx_f, const float* vy_f, int H, int W,
+                              int batch, int cap, const int32_t* n_valid, const int32_t* labels,
+                              const int32_t* indices, int max_clusters, double* summary);
+
+/* ---- BEV rasterisation -------------------------------------------------------------
+ * Replaces compute_bev_grid, main.py:98-126.  pts: n points in the given layout;
+ * nx, ny = len(np.arange(lo, hi, step)) (datmo_bev_bins).  bev: uint8 [nx][ny],
+ * axis 0 = x.  Bit-exact with the reference for finite inputs. */
+int datmo_bev_bins(double lo, double hi, double step);
+int datmo_bev_rasterize_dev(datmo_handle_t h, const void* pts, int layout, int64_t n, double res_x,
+                            double res_y, double x_lo, double y_lo, int nx, int ny, double a, double b,
+                            double h_max, uint8_t* bev);
+int datmo_bev_rasterize_host(datmo_handle_t h, const void* pts, int layout, int64_t n, double res_x,
+                             double res_y, double x_lo, double y_lo, int nx, int ny, double a, double b,
+                             double h_max, uint8_t* bev);
+
+/* ---- RANSAC ground plane -------------------------------------------------------------
+ * Replaces flipped_pcd.segment_plane(0.5, 5, 5000), main.py:73 (Open3D).  Scores
+ * num_iterations plane hypotheses (ransac_n samples each, drawn by the counter-based
+ * hash documented in oracle/ransac_np.py) against all n points in fp64.
+ * Outputs (device): plane double[4] = the winning hypothesis; refit double[4] = plane
+ * refit on its inliers; inlier_mask uint8[n]; best int32[2] = {hypothesis index,
+ * inlier count}.  hyp_planes (double[num_iterations][4]), hyp_count (int32[..]) and
+ * hyp_err (double[..]) may be NULL; when given they receive every hypothesis. */
+int datmo_ransac_ground_dev(datmo_handle_t h, const void* pts, int layout, int64_t n, int flip_x,
+                            double distance_threshold, int ransac_n, int num_iterations, uint64_t seed,
+                            double* plane, double* refit, uint8_t* inlier_mask, int32_t* best,
+                            double* hyp_planes, int32_t* hyp_count, double* hyp_err);
+
+/* ---- fused per-frame preprocessing ---------------------------------------------------
+ * Replaces preprocess_pcd after the file read, main.py:65-92: flip x, RANSAC ground
+ * removal, ROI crop (closed intervals, main.py:30-36), x expansion copies with Gaussian
+ * noise (main.py:38-57) and rasterisation.  pts: float [n][4] (device).  noise: double
+ * [n][expansion][3] (device) added to the copies of point i — or NULL to draw
+ * N(0, noise_std) on the device from seed.  ground_mask: optional uint8[n] (device);
+ * when given, RANSAC is skipped and these points are dropped instead.
+ * n_roi (host int64*, may be NULL) receives the number of points inside the ROI;
+ * returns DATMO_E_EMPTY when it is zero (the reference returns None, main.py:84-86).
+ * Synchronises. */
+int datmo_preprocess_dev(datmo_handle_t h, const float* pts, int64_t n, int flip_x,
+                         double distance_threshold, int ransac_n, int num_iterations, uint64_t seed,
+                         const uint8_t* ground_mask, const double roi[6], int expansion,
+                         double noise_std, const double* noise, double res_x, double res_y, double x_lo,
+                         double y_lo, int nx, int ny, double h_max, uint8_t* bev, int64_t* n_roi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DATMO_B200_H */

@@ -1,0 +1,130 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference functions
+(/root/reference/Optical_flow/main.py, imported through oracle/ref_loader.py with
+stubbed open3d / matplotlib / shapely) on small seeded inputs.
+
+Run in the build container only (the reference is not on the GPU box):
+    python tests/golden/make_golden.py
+Library versions used are recorded inside each file.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from datmo_using_optical_flow_b200 import synth  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def versions():
+    import cv2
+    import sklearn
+    return np.array([f"numpy {np.__version__}", f"cv2 {cv2.__version__}", f"sklearn {sklearn.__version__}"])
+
+
+def bev_cases():
+    rng = np.random.default_rng(11)
+    cases = {}
+    res, xr, yr = (0.5, 0.5), (-10.0, 10.0), (-8.0, 8.0)
+    # (a) ordinary cloud, z > 0, some points outside the grid and in the (lo - w, lo) sliver
+    p = np.column_stack([rng.uniform(-11, 11, 6000), rng.uniform(-9, 9, 6000), rng.uniform(0.05, 3.0, 6000)])
+    cases["a"] = (p, res, xr, yr, 5.0)
+    # (b) roof-mounted sensor: most z < 0 (uint8 wrap-around), x10 expansion noise
+    base = np.column_stack([rng.uniform(-9, 9, 500), rng.uniform(-7, 7, 500), rng.uniform(-2.4, 0.8, 500)])
+    p = np.repeat(base, 10, axis=0) + rng.normal(scale=0.01, size=(5000, 3))
+    cases["b"] = (p, res, xr, yr, 2.0)
+    # (c) every occupied cell <= 0 -> max = 0 -> all zeros
+    p = np.column_stack([rng.uniform(-9, 9, 800), rng.uniform(-7, 7, 800), np.full(800, -1.25)])
+    cases["c"] = (p, res, xr, yr, 2.0)
+    # (d) non-square resolution, single point, points exactly on bin edges
+    p = np.array([[0.0, 0.0, 1.0], [-10.0, -8.0, 0.5], [9.999, 7.999, 2.0], [-10.2, 0.0, 3.0], [10.0, 0.0, 3.0],
+                  [0.25, 0.2, 0.7], [0.25, 0.2, 0.9]])
+    cases["d"] = (p, (0.25, 0.2), xr, yr, 5.0)
+    return cases
+
+
+def main():
+    ref = ref_loader.load_reference_main()
+    ver = versions()
+
+    # ---- BEV ---------------------------------------------------------------------------
+    out = {"versions": ver}
+    for name, (p, res, xr, yr, hmax) in bev_cases().items():
+        with ref_loader.quiet(), np.errstate(all="ignore"):
+            g = ref.compute_bev_grid(p, list(res), list(xr), list(yr), h_max=hmax)
+        out[f"{name}_points"] = p
+        out[f"{name}_params"] = np.array([res[0], res[1], xr[0], xr[1], yr[0], yr[1], hmax])
+        out[f"{name}_bev"] = g
+    pts = np.array([[-11.0, 0, 0], [-10.0, -10.0, -3.0], [10.0, 10.0, 1.0], [0, 0, 1.0000001], [0, 0, 0.5], [3, 11, 0]])
+    out["roi_points"] = pts
+    out["roi_bounds"] = np.array([-10, 10, -10, 10, -3, 1.0])
+    out["roi_out"] = ref.filter_points_in_roi(pts, [-10, 10, -10, 10, -3, 1])
+    np.savez_compressed(os.path.join(OUT, "bev.npz"), **out)
+
+    # ---- flow -> velocity -> masks -> dbscan -> clusters, through the reference functions ----
+    out = {"versions": ver}
+    xr, yr = [-16.0, 16.0], [-12.0, 12.0]
+    pairs = {"tex": synth.textured_pair(5, 96, 128, shift=(2, -3)), "blob": synth.bev_pair(3, 120, 160)}
+    for name, (a, b) in pairs.items():
+        with ref_loader.quiet():
+            vx, vy, ang = ref.compute_velocity_vectors(a, b, xr, yr, 1.0)
+            mask = ref.continuity_mask(vx, vy, 0.2)
+        vx_f = vx * mask
+        vy_f = vy * mask
+        mag = np.sqrt(vx_f ** 2 + vy_f ** 2)
+        dvx_dy, dvx_dx = np.gradient(vx_f)
+        dvy_dy, dvy_dx = np.gradient(vy_f)
+        ang_f = dvy_dx - dvx_dy
+        valid = mag > 0.1
+        out[f"{name}_a"], out[f"{name}_b"] = a, b
+        out[f"{name}_vx"], out[f"{name}_vy"], out[f"{name}_ang"] = vx, vy, ang
+        out[f"{name}_mask"] = mask.astype(np.uint8)
+        out[f"{name}_angf"] = ang_f
+        out[f"{name}_valid"] = valid
+        if valid.sum() >= 12:
+            with ref_loader.quiet():
+                labels, idx = ref.dbscan_clustering(vx_f, vy_f, valid, eps=5.0, min_samples=3)
+                cl = ref.extract_cluster_data(labels, idx, vx_f, vy_f)
+            out[f"{name}_labels"], out[f"{name}_indices"] = labels, idx
+            keys = sorted(cl)
+            out[f"{name}_cl_keys"] = np.array(keys)
+            out[f"{name}_cl_meas"] = np.array([cl[k]["measurement"] for k in keys], dtype=np.float64)
+            out[f"{name}_cl_eig"] = np.array([np.sort(np.real(cl[k]["eigenvalues"])) for k in keys])
+    out["ranges"] = np.array(xr + yr)
+    np.savez_compressed(os.path.join(OUT, "flow_chain.npz"), **out)
+
+    # ---- DBSCAN on a crafted field with border points and several (eps, min_samples) ----------
+    out = {"versions": ver}
+    rng = np.random.default_rng(21)
+    H, W = 48, 64
+    vx = np.zeros((H, W), np.float32)
+    vy = np.zeros((H, W), np.float32)
+    for _ in range(9):
+        y, x = rng.integers(2, H - 12), rng.integers(2, W - 14)
+        h, w = rng.integers(2, 10), rng.integers(2, 12)
+        vx[y:y + h, x:x + w] = rng.uniform(-3, 3)
+        vy[y:y + h, x:x + w] = rng.uniform(-3, 3)
+    vx += (rng.uniform(-0.4, 0.4, (H, W)) * (vx != 0)).astype(np.float32)
+    sp = rng.uniform(size=(H, W)) < 0.03
+    vx[sp] = rng.uniform(-2, 2, sp.sum()).astype(np.float32)
+    vy[sp] = rng.uniform(-2, 2, sp.sum()).astype(np.float32)
+    vxd, vyd = vx.astype(np.float64), vy.astype(np.float64)
+    valid = np.sqrt(vxd ** 2 + vyd ** 2) > 0.1
+    out["vx"], out["vy"], out["valid"] = vx, vy, valid
+    for i, (eps, ms) in enumerate([(5.0, 3), (1.0, 5), (1.5, 4), (2.9, 8), (3.0, 2)]):
+        with ref_loader.quiet():
+            labels, idx = ref.dbscan_clustering(vxd, vyd, valid, eps=eps, min_samples=ms)
+        out[f"labels_{i}"] = labels
+        out[f"params_{i}"] = np.array([eps, ms])
+    out["indices"] = idx
+    np.savez_compressed(os.path.join(OUT, "dbscan.npz"), **out)
+    for f in ("bev.npz", "flow_chain.npz", "dbscan.npz"):
+        print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()
