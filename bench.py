@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — BEV frame-pairs/sec through the B200 hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): independent
+1024x1024 uint8 BEV frame pairs, sharded across ranks with no data-path collective.  One step =
+one pass of the hot path over one batch of pairs resident in HBM: Farneback pyramid (reference
+parameters, Optical_flow/main.py:132-140) -> velocity grid -> continuity mask -> moving-cell
+threshold -> DBSCAN labels -> cluster summaries.  `value` = pairs/s over all ranks (device-timed,
+max over ranks); `e2e` = the same chain through the host-buffer API with the H2D / D2H copies
+inside the timed region.  `--impl reference` times the reference's own CPU call sequence
+(oracle/reference_port.py: cv2 + numpy + sklearn exactly as main.py calls them) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# reference parameters (config.yaml masks / dbscan_params; Farneback hard-coded in main.py:132-140)
+ALPHA_CONT = 0.2
+EPS = 5.0
+MIN_SAMPLES = 3
+FB = dict(pyr_scale=0.3, levels=5, winsize=15, iterations=5, poly_n=5, poly_sigma=5.0, flags=0)
+METRIC = "bev_frame_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def algorithmic_bytes(H, W, fb=FB):
+    """stage-fused model, f32 arrays, each logical array crossing HBM once per
+    producing / consuming stage.  Returns (A per pair, bytes of the flow-iteration launches per pair)."""
+    from oracle import farneback_np
+    layers = farneback_np.level_plan(H, W, fb["pyr_scale"], fb["levels"])
+    N0 = H * W
+    sumN = sum(l["w"] * l["h"] for l in layers)
+    up = sum(l["w"] * l["h"] for l in layers[1:])      # every layer but the coarsest reads an upsampled flow
+    iters = fb["iterations"]
+    A = len(layers) * 8 * N0 + 40 * sumN + iters * 56 * sumN + 8 * up
+    return A, iters * 56 * sumN, len(layers)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as fh:
+            for line in fh:
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's call sequence on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, H, W, repeat = args
+    import cv2
+    cv2.setNumThreads(1)
+    from datmo_using_optical_flow_b200 import synth
+    from oracle import reference_port
+    a, b = synth.bev_pair(seed, H, W)
+    rng = [-0.05 * W, 0.05 * W]
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(repeat):
+        out = reference_port.flow_to_clusters(a, b, rng, [-0.05 * H, 0.05 * H], 1.0, ALPHA_CONT, EPS, MIN_SAMPLES)
+        n += len(out["labels"])
+    return time.perf_counter() - t0, n
+
+
+def cpu_pairs_per_sec(H, W, cores, rounds, seed0=0, pool=None):
+    """`cores` worker processes (cv2 single-threaded in each: OpenCV's Farneback does not scale with
+    threads), one pair per worker per round; returns (pairs/s, wall seconds)."""
+    import multiprocessing as mp
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores)
+    try:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(seed0 + i, H, W, rounds) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
+    return cores * rounds / wall, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    H = W = args.size
+    cores = os.cpu_count() or 1
+    pool = mp.get_context("spawn").Pool(cores)
+    try:
+        for i in range(args.warmup):
+            cpu_pairs_per_sec(H, W, cores, 1, seed0=1000 + i * cores, pool=pool)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            cpu_pairs_per_sec(H, W, cores, 1, seed0=i * cores, pool=pool)
+        wall = time.perf_counter() - t0
+    finally:
+        pool.close()
+        pool.join()
+    pairs = cores * args.steps
+    value = pairs / wall
+    sample = f"{cores} pairs per step (one per worker process, cv2 single-threaded), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cores),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": f"BASELINE configs[2]: independent {args.size}x{args.size} uint8 BEV frame pairs "
+                        "(20-200 rectangles, integer shifts <= 3 px), Farneback (pyr 0.3, 5 levels -> 3 layers, "
+                        "winsize 15, 5 iterations, poly 5/5.0) -> velocity -> continuity mask -> mag>0.1 -> "
+                        "DBSCAN(eps 5, min_samples 3) -> cluster summaries",
+            "size": args.size, "pairs_per_step_per_gpu": batch, "pool_pairs_per_gpu": args.pool,
+            "l2": "step working set (~70 MB/pair of f32 planes) and the rotating input pool exceed the 126 MB L2",
+            "sharding": "pairs sharded across ranks, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from datmo_using_optical_flow_b200 import synth
+    from datmo_using_optical_flow_b200.engine import Engine, farneback_params
+
+    H = W = args.size
+    B = args.batch
+    eng = Engine(local)
+    params = farneback_params(**FB)
+    px = py = 0.1
+    # resident input pool: each rank owns a disjoint slice of the pair index space
+    n_pool = max(args.pool, B)
+    prev_h, next_h = synth.bev_pairs(rank * n_pool, n_pool, H, W)
+    prev_pin = torch.from_numpy(prev_h).pin_memory()
+    next_pin = torch.from_numpy(next_h).pin_memory()
+    prev_d = prev_pin.cuda(non_blocking=True)
+    next_d = next_pin.cuda(non_blocking=True)
+    flow_buf = torch.empty((B, H, W, 2), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    n_batches = n_pool // B
+
+    def step(i):
+        s = (i % n_batches) * B
+        return eng.flow_pipeline(prev_d[s:s + B], next_d[s:s + B], px, py, ALPHA_CONT, EPS, MIN_SAMPLES, params,
+                                 cap=args.cap, max_clusters=args.max_clusters, keep_flow=False, flow_buf=flow_buf)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ---------------------------------------------------------------
+    for i in range(args.warmup):
+        res = step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile(True)
+    eng.profile_reset()
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with eng.on_stream():
+        ev0.record()
+    for i in range(args.steps):
+        res = step(args.warmup + i)
+    with eng.on_stream():
+        ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    prof = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    n_valid_mean = float(res.n_valid.float().mean().item())
+    n_clusters_mean = float(res.n_clusters.float().mean().item())
+    truncated = bool((res.n_valid > args.cap).any().item())
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    lc = torch.tensor([launches], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lc, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    # ---- end to end through the host-buffer API -------------------------------------------------------
+    h2d = 2 * B * H * W
+    d2h_total = 0
+
+    def e2e_step(i):
+        nonlocal d2h_total
+        s = (i % n_batches) * B
+        with eng.on_stream():
+            a = prev_pin[s:s + B].cuda(non_blocking=True)
+            b = next_pin[s:s + B].cuda(non_blocking=True)
+            r = eng.flow_pipeline(a, b, px, py, ALPHA_CONT, EPS, MIN_SAMPLES, params, cap=args.cap,
+                                  max_clusters=args.max_clusters, keep_flow=False, flow_buf=flow_buf)
+            counts = torch.stack([r.n_valid, r.n_clusters]).cpu()          # sync point: sizes of the ragged results
+            nmax = int(min(int(counts[0].max()), args.cap))
+            kmax = int(min(int(counts[1].max()), args.max_clusters))
+            labels = r.labels[:, :nmax].contiguous().cpu()
+            indices = r.indices[:, :nmax].contiguous().cpu()
+            summary = r.summary[:, :kmax].contiguous().cpu()
+        d2h_total += counts.numel() * 4 + labels.numel() * 4 + indices.numel() * 4 + summary.numel() * 8
+        return labels, indices, summary
+
+    for i in range(max(1, args.warmup // 2)):
+        e2e_step(i)
+    barrier()
+    d2h_total = 0
+    e2e_steps = max(1, args.steps // 2)
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(args.warmup + i)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(te.item())
+
+    # ---- the only collective: gather per-shard metrics (off the hot path) -------------------------------
+    shard = torch.tensor([n_valid_mean, n_clusters_mean, float(truncated)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        gathered = [torch.empty_like(shard) for _ in range(world)]
+        dist.all_gather(gathered, shard)
+        shard_stats = torch.stack(gathered).cpu().numpy()
+    else:
+        shard_stats = shard.cpu().numpy()[None]
+
+    if rank == 0:
+        A, iter_bytes, n_layers = algorithmic_bytes(H, W)
+        peak, peak_src = measured_peaks()
+        it = prof["flow_iter"]
+        it_ms = it["ms"] / max(it["launches"], 1)
+        # algorithmic bytes of the flow-iteration launches of one step / their summed device time
+        achieved = (iter_bytes * B * args.steps) / (it["ms"] / 1e3) / 1e9 if it["ms"] > 0 else 0.0
+        whole = A * value / world / 1e9
+        stage_ms = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["launches"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, B),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(d2h_total / e2e_steps), "steps": e2e_steps,
+                    "what": "pinned host uint8 pairs -> H2D -> flow..clusters -> D2H of counts, labels, indices, "
+                            "cluster summaries"},
+            "gpu_launches": int(lc.item()),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_flow_iter<fused> (updateMatrices + box blur + solve)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "bytes_per_launch_model": "56 B x layer pixels x pairs (R0 20 + R1 20 + flow 8 in, flow 8 out)",
+                         "avg_launch_ms": it_ms, "launches": it["launches"],
+                         "whole_pipeline": {"A_bytes_per_pair": A, "achieved_gbs_per_gpu": whole,
+                                            "frac": whole / peak}},
+            "stage_ms_per_step": stage_ms,
+            "moving_cells_per_pair": float(shard_stats[:, 0].mean()),
+            "clusters_per_pair": float(shard_stats[:, 1].mean()),
+            "cap_truncated": bool(shard_stats[:, 2].any()),
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            rounds = args.cpu_rounds
+            v, wall = cpu_pairs_per_sec(H, W, cores, rounds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{cores * rounds} pairs of the same workload ({cores} worker processes x "
+                                              f"{rounds}, cv2 single-threaded each), {wall:.1f} s wall, "
+                                              "oracle/reference_port.flow_to_clusters"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--pool", type=int, default=128, help="resident frame pairs per GPU")
+    ap.add_argument("--cap", type=int, default=524288, help="max moving cells per pair kept by DBSCAN")
+    ap.add_argument("--max-clusters", type=int, default=1024)
+    ap.add_argument("--cpu-rounds", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

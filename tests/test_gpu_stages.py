@@ -1,0 +1,250 @@
+"""GPU parity of the non-Farneback stages, through the C ABI: BEV rasteriser (bit-exact), velocity /
+masks (exact), DBSCAN (labels identical to sklearn's), cluster summaries, RANSAC scoring, fused
+preprocessing."""
+import numpy as np
+import pytest
+import torch
+
+from datmo_using_optical_flow_b200 import main, synth
+from oracle import bev_np, cluster_np, dbscan_np, masks_np, ransac_np, reference_port
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+# ---- BEV ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+def test_bev_golden_bit_exact(engine, golden, case):
+    g = golden("bev.npz")
+    p = g[f"{case}_points"]
+    rx, ry, x0, x1, y0, y1, hmax = (float(v) for v in g[f"{case}_params"])
+    got = main.compute_bev_grid(p, [rx, ry], [x0, x1], [y0, y1], h_max=hmax, engine=engine)
+    assert got.dtype == np.uint8 and np.array_equal(got, g[f"{case}_bev"])
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
+def test_bev_large_cloud_bit_exact_both_layouts(engine, cfg):
+    c = synth.SWEEP_CONFIGS[cfg]
+    pts = synth.lidar_sweep(0, 3, c["beams"], c["n_points"], c["n_movers"])
+    rng = np.random.default_rng(1)
+    p64 = np.repeat(pts[:, :3].astype(np.float64), 10, axis=0) + rng.normal(scale=0.01, size=(len(pts) * 10, 3))
+    want = bev_np.compute_bev_grid(p64, c["grid_resolution"], c["x_range"], c["y_range"], h_max=2.0)
+    got = main.compute_bev_grid(p64, c["grid_resolution"], c["x_range"], c["y_range"], h_max=2.0, engine=engine)
+    assert got.shape == want.shape and np.array_equal(got, want), int((got != want).sum())
+    # float32 xyzw layout: same values as the f64 view of the f32 points
+    want32 = bev_np.compute_bev_grid(pts[:, :3].astype(np.float64), c["grid_resolution"], c["x_range"], c["y_range"], h_max=2.0)
+    got32 = main.compute_bev_grid(dev(pts), c["grid_resolution"], c["x_range"], c["y_range"], h_max=2.0, engine=engine)
+    assert np.array_equal(host(got32), want32)
+
+
+def test_bev_empty_and_ragged(engine):
+    got = main.compute_bev_grid(np.zeros((0, 3)), [0.5, 0.5], [-2, 2], [-1, 1], engine=engine)
+    assert got.shape == (8, 4) and not got.any()
+    one = np.array([[0.1, 0.1, 1.0]])
+    got = main.compute_bev_grid(one, [0.5, 0.5], [-2, 2], [-1, 1], engine=engine)
+    assert np.array_equal(got, bev_np.compute_bev_grid_loops(one, [0.5, 0.5], [-2, 2], [-1, 1]))
+
+
+# ---- velocity / masks --------------------------------------------------------------------------------
+def test_velocity_and_masks_exact(engine, golden):
+    g = golden("flow_chain.npz")
+    xr, yr = [float(v) for v in g["ranges"][:2]], [float(v) for v in g["ranges"][2:]]
+    for name in ("tex", "blob"):
+        vx, vy = g[f"{name}_vx"], g[f"{name}_vy"]
+        H, W = vx.shape
+        # feed the golden velocities back as a "flow" with unit pixel size: every derived grid must be exact
+        m = main.continuity_mask(vx, vy, 0.2, engine=engine)
+        assert m.dtype == np.int64 and np.array_equal(m.astype(np.uint8), g[f"{name}_mask"])
+        vxf, vyf, mag, angf, valid = main.moving_cell_filter(vx, vy, 0.2, engine=engine)
+        ovxf, ovyf, omag, oangf, ovalid = masks_np.moving_cell_filter(vx, vy, masks_np.continuity_mask(vx, vy, 0.2))
+        assert vxf.dtype == np.float64 and np.array_equal(vxf, ovxf) and np.array_equal(vyf, ovyf)
+        assert np.array_equal(valid, g[f"{name}_valid"])
+        assert np.array_equal(mag, omag)
+        assert np.array_equal(angf.astype(np.float32), g[f"{name}_angf"].astype(np.float32))
+    # pixel-size scaling and curl from a raw flow field
+    rng = np.random.default_rng(0)
+    flow = rng.uniform(-4, 4, (2, 50, 70, 2)).astype(np.float32)
+    vm = engine.velocity_mask(dev(flow), 0.25, 0.2, 0.2)
+    for b in range(2):
+        ovx, ovy, oang = masks_np.flow_to_velocity(flow[b], [0.0, 17.5], [0.0, 10.0])     # 17.5/70 = .25, 10/50 = .2
+        assert np.array_equal(host(vm["vx"])[b], ovx) and np.array_equal(host(vm["vy"])[b], ovy)
+        assert np.array_equal(host(vm["ang"])[b], oang)
+        om = masks_np.continuity_mask(ovx, ovy, 0.2)
+        assert np.array_equal(host(vm["mask"])[b], om.astype(np.uint8))
+        valid = masks_np.moving_cell_filter(ovx, ovy, om)[4]
+        assert np.array_equal(host(vm["valid"])[b].astype(bool), valid)
+        assert int(host(vm["n_valid"])[b]) == int(valid.sum())
+
+
+# ---- DBSCAN ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("i", range(5))
+def test_dbscan_golden_labels_identical(engine, golden, i):
+    g = golden("dbscan.npz")
+    eps, ms = g[f"params_{i}"]
+    labels, idx = main.dbscan_clustering(g["vx"].astype(np.float64), g["vy"].astype(np.float64), g["valid"],
+                                         eps=float(eps), min_samples=int(ms), engine=engine)
+    assert labels.dtype == np.intp and idx.dtype == np.int64
+    assert np.array_equal(idx, g["indices"])
+    assert np.array_equal(labels, g[f"labels_{i}"])
+    assert dbscan_np.same_partition(labels, g[f"labels_{i}"])
+
+
+def test_dbscan_random_fields_vs_sklearn_batched(engine):
+    rng = np.random.default_rng(7)
+    B, H, W = 6, 90, 130
+    vx = np.where(rng.uniform(size=(B, H, W)) < 0.2, rng.uniform(-2, 2, (B, H, W)), 0).astype(np.float32)
+    vy = np.where(vx != 0, rng.uniform(-2, 2, (B, H, W)), 0).astype(np.float32)
+    valid = np.sqrt(vx.astype(np.float64) ** 2 + vy.astype(np.float64) ** 2) > 0.1
+    for eps, ms in [(5.0, 3), (1.0, 2), (2.5, 6), (1.5, 4)]:
+        n_valid, labels, indices, n_clusters = engine.dbscan_grid(dev(vx), dev(vy), dev(valid.astype(np.uint8)), eps, ms)
+        n_valid, labels, indices, n_clusters = (host(t) for t in (n_valid, labels, indices, n_clusters))
+        for b in range(B):
+            want, widx = dbscan_np.dbscan_clustering_sklearn(vx[b].astype(np.float64), vy[b].astype(np.float64), valid[b], eps, ms)
+            n = n_valid[b]
+            assert n == len(want)
+            assert np.array_equal(indices[b, :n], widx)
+            assert np.array_equal(labels[b, :n], want), (eps, ms, b)
+            assert n_clusters[b] == (want.max() + 1 if len(want) and want.max() >= 0 else 0)
+
+
+def test_dbscan_large_grid_vs_grid_rule_oracle(engine):
+    """cfg3-sized grid, sparse moving cells; the oracle grid rule is itself pinned to sklearn on CPU."""
+    rng = np.random.default_rng(3)
+    H = W = 1024
+    vx = np.zeros((H, W), np.float32)
+    vy = np.zeros((H, W), np.float32)
+    for _ in range(60):
+        y, x = rng.integers(0, H - 40), rng.integers(0, W - 40)
+        h, w = rng.integers(3, 30), rng.integers(3, 30)
+        vx[y:y + h, x:x + w] = rng.uniform(-1, 1) + rng.uniform(-0.05, 0.05, (h, w))
+        vy[y:y + h, x:x + w] = rng.uniform(-1, 1) + rng.uniform(-0.05, 0.05, (h, w))
+    valid = np.sqrt(vx.astype(np.float64) ** 2 + vy.astype(np.float64) ** 2) > 0.1
+    want, widx = dbscan_np.dbscan_grid(vx, vy, valid, 5.0, 3)
+    labels, idx = main.dbscan_clustering(vx, vy, valid, eps=5.0, min_samples=3, engine=engine)
+    assert np.array_equal(idx, widx) and np.array_equal(labels, want)
+
+
+def test_dbscan_empty_mask_raises_like_sklearn(engine):
+    z = np.zeros((16, 16), np.float32)
+    with pytest.raises(ValueError):
+        main.dbscan_clustering(z, z, np.zeros((16, 16), bool), engine=engine)
+
+
+def test_dbscan_capacity_truncates_but_counts(engine):
+    vx = np.ones((8, 8), np.float32)
+    n_valid, labels, indices, _ = engine.dbscan_grid(dev(vx), dev(vx), dev(np.ones((8, 8), np.uint8)), 1.0, 2, cap=10)
+    assert int(host(n_valid)[0]) == 64 and labels.shape == (1, 10)
+    assert (host(labels)[0] == 0).all()
+
+
+# ---- clusters ---------------------------------------------------------------------------------------
+def test_cluster_summary_vs_oracle(engine, golden):
+    g = golden("flow_chain.npz")
+    mask = g["blob_mask"].astype(np.int64)
+    vx_f, vy_f = g["blob_vx"] * mask, g["blob_vy"] * mask
+    got = main.extract_cluster_data(g["blob_labels"], g["blob_indices"], vx_f, vy_f, engine=engine)
+    want = cluster_np.extract_cluster_data(g["blob_labels"], g["blob_indices"], vx_f, vy_f)
+    assert sorted(got) == sorted(want) == list(g["blob_cl_keys"])
+    for k in want:
+        np.testing.assert_allclose(got[k]["measurement"], want[k]["measurement"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(np.sort(got[k]["eigenvalues"]), np.sort(want[k]["eigenvalues"]), rtol=1e-7, atol=1e-7,
+                                   equal_nan=True)
+    with pytest.raises(ValueError):
+        main.extract_cluster_data(g["blob_labels"][:-1], g["blob_indices"], vx_f, vy_f, engine=engine)
+
+
+def test_flow_to_clusters_chain_vs_reference_port(engine):
+    a, b = synth.bev_pair(12, 240, 320)
+    xr, yr = [-16.0, 16.0], [-12.0, 12.0]
+    labels, indices, clusters = main.flow_to_clusters(a, b, xr, yr, 1.0, 0.2, 5.0, 3, engine=engine)
+    want = reference_port.flow_to_clusters(a, b, xr, yr, 1.0, 0.2, 5.0, 3)
+    # flows agree to ~1e-4, so cells within that of a threshold may flip: compare with a guard band
+    sym = len(set(map(tuple, indices.tolist())) ^ set(map(tuple, want["indices"].tolist())))
+    assert sym <= max(3, 0.002 * len(want["indices"])), (sym, len(want["indices"]))
+    assert abs(len(clusters) - len(want["clusters"])) <= 1
+
+
+# ---- RANSAC ------------------------------------------------------------------------------------------
+def test_ransac_hypotheses_and_scores_vs_oracle(engine):
+    pts = synth.lidar_sweep(1, 0, 32, 20_000, 1)
+    n = len(pts)
+    iters = 700
+    out = engine.ransac_ground(dev(pts), 0.5, 5, iters, seed=11, flip_x=True, return_hypotheses=True)
+    planes, cnt, err = host(out["hyp_planes"]), host(out["hyp_count"]), host(out["hyp_err"])
+    p64 = pts[:, :3].astype(np.float64)
+    p64[:, 0] = -p64[:, 0]
+    idx, ok = ransac_np.sample_indices(11, iters, 5, n)
+    assert ok.all()
+    want_planes = ransac_np.plane_from_points(p64[idx])
+    np.testing.assert_allclose(planes, want_planes, rtol=0, atol=1e-9)
+    # scoring is exact given the device's own planes
+    wc, we = ransac_np.score_planes(p64, planes, 0.5)
+    assert np.array_equal(cnt, wc)
+    np.testing.assert_allclose(err, we, rtol=1e-10, atol=1e-9)
+    best = host(out["best"])
+    assert best[0] == ransac_np.select_best(wc, we) and best[1] == wc[best[0]]
+    assert np.array_equal(host(out["plane"]), planes[best[0]])
+    mask = host(out["inlier_mask"]).astype(bool)
+    assert np.array_equal(mask, ransac_np.point_plane_distance(p64, planes[best[0]]) < 0.5)
+    refit = host(out["refit"])
+    want_refit = ransac_np.plane_from_points(p64[mask][None])[0]
+    np.testing.assert_allclose(refit * np.sign(refit[2]), want_refit * np.sign(want_refit[2]), atol=1e-7)
+    # scene-level: the planted ground plane z = -2.5 is found
+    nrm = refit[:3] * np.sign(refit[2])
+    assert np.degrees(np.arccos(np.clip(nrm[2], -1, 1))) < 0.5 and abs(abs(refit[3]) - 2.5) < 0.05
+
+
+def test_ransac_f64_layout_and_three_point_model(engine):
+    rng = np.random.default_rng(2)
+    p = np.column_stack([rng.uniform(-20, 20, 5000), rng.uniform(-20, 20, 5000), 1.0 + rng.normal(0, 0.01, 5000)])
+    p[:1000, 2] = rng.uniform(2, 8, 1000)
+    out = engine.ransac_ground(dev(p), 0.3, 3, 200, seed=5, return_hypotheses=True)
+    planes = host(out["hyp_planes"])
+    idx, ok = ransac_np.sample_indices(5, 200, 3, len(p))
+    np.testing.assert_allclose(planes, ransac_np.plane_from_points(p[idx]), atol=1e-9)
+    wc, _ = ransac_np.score_planes(p, planes, 0.3)
+    assert np.array_equal(host(out["hyp_count"]), wc)
+    assert host(out["inlier_mask"])[1000:].mean() > 0.99
+
+
+# ---- fused preprocessing --------------------------------------------------------------------------------
+def test_preprocess_fused_vs_oracle_given_noise_and_ground(engine):
+    c = synth.SWEEP_CONFIGS["cfg1"]
+    pts = synth.lidar_sweep(2, 1, c["beams"], c["n_points"], c["n_movers"])
+    n = len(pts)
+    rng = np.random.default_rng(4)
+    noise = rng.normal(scale=0.01, size=(n, 10, 3))
+    ground = np.abs(pts[:, 2] + 2.5) < 0.5
+    roi = [-50, 50, -50, 50, -3, 1]
+    got = main.preprocess_points(pts, c["grid_resolution"], c["x_range"], c["y_range"], 2.0, roi, noise=noise,
+                                 ground_mask=ground, engine=engine)
+    p64 = pts[:, :3].astype(np.float64)
+    p64[:, 0] = -p64[:, 0]
+    keep = (~ground) & (p64[:, 0] >= -50) & (p64[:, 0] <= 50) & (p64[:, 1] >= -50) & (p64[:, 1] <= 50) & \
+           (p64[:, 2] >= -3) & (p64[:, 2] <= 1)
+    want = reference_port.preprocess_points(pts, c["grid_resolution"], c["x_range"], c["y_range"], 2.0, roi,
+                                            noise[keep].reshape(-1, 3), ground_mask=ground)
+    assert got.shape == want.shape and np.array_equal(got, want), int((got != want).sum())
+
+
+def test_preprocess_with_device_ransac_and_device_noise(engine):
+    c = synth.SWEEP_CONFIGS["cfg1"]
+    pts = synth.lidar_sweep(2, 2, c["beams"], c["n_points"], c["n_movers"])
+    roi = [-50, 50, -50, 50, -3, 1]
+    bev = main.preprocess_points(pts, c["grid_resolution"], c["x_range"], c["y_range"], 2.0, roi, seed=3, engine=engine)
+    assert bev is not None and bev.shape == (400, 400) and bev.dtype == np.uint8 and bev.max() == 255
+    occ = (bev > 0).mean()
+    assert 0.001 < occ < 0.2        # ground removed: only objects remain
+    bev2 = main.preprocess_points(pts, c["grid_resolution"], c["x_range"], c["y_range"], 2.0, roi, seed=3, engine=engine)
+    assert (bev != bev2).mean() < 1e-3     # same seed -> same noise; atomics may flip a last bit, never more
+    # empty ROI -> None, like the reference (main.py:84-86)
+    assert main.preprocess_points(pts, c["grid_resolution"], c["x_range"], c["y_range"], 2.0,
+                                  [1000, 1001, 1000, 1001, 0, 1], engine=engine) is None
