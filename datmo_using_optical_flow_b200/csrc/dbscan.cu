@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(256) k_core(const float* __restrict__ vx, cons
                 int xx = x + dc;
                 if (xx < 0 || xx >= W) continue;
                 size_t q = base + static_cast<size_t>(yy) * W + xx;
-                if (valid[q] && within_eps(dr, dc, vx0, vy0, vx[q], vy[q], eps2)) ++cnt;
+                if (valid[q] && within_eps(dr, dc, vx0, vy0, vx[q], vy[q], eps2)) {
+                    if (++cnt >= min_samples) break;
+                }
             }
         }
         st = cnt >= min_samples ? 2 : 1;
@@ -190,9 +192,37 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_union(const float* __restrict__ vx, const float* __restrict__ vy,
-                                               const uint8_t* __restrict__ state, int H, int W, int r, double eps2,
-                                               int32_t* __restrict__ parent) {
+// Union pass 1: only the four preceding 8-neighbours.  In dense moving regions this
+// already joins almost every cell of a component with ~4 cheap links per cell.
+__global__ void __launch_bounds__(256) k_union_near(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                    const uint8_t* __restrict__ state, int H, int W, int r,
+                                                    double eps2, int32_t* __restrict__ parent) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W || r < 1) return;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const int o = y * W + x;
+    if (state[base + o] != 2) return;
+    const float vx0 = vx[base + o], vy0 = vy[base + o];
+    int32_t* par = parent + base;
+    const int ndr[4] = {0, -1, -1, -1}, ndc[4] = {-1, -1, 0, 1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int yy = y + ndr[k], xx = x + ndc[k];
+        if (yy < 0 || xx < 0 || xx >= W) continue;
+        const int q = yy * W + xx;
+        if (state[base + q] == 2 && within_eps(ndr[k], ndc[k], vx0, vy0, vx[base + q], vy[base + q], eps2))
+            uf_union(par, o, q);
+    }
+}
+
+// Union pass 2 (after a flatten): the rest of the preceding half-window.  parent[] now
+// holds each cell's pass-1 root, so "same parent" proves "same component" from one
+// cached load and skips both the fp64 distance test and the union; only the few pairs
+// that bridge different pass-1 components reach the atomic path.
+__global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                   const uint8_t* __restrict__ state, int H, int W, int r,
+                                                   double eps2, int32_t* __restrict__ parent) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
@@ -201,17 +231,19 @@ __global__ void __launch_bounds__(256) k_union(const float* __restrict__ vx, con
     if (state[base + o] != 2) return;
     const float vx0 = vx[base + o], vy0 = vy[base + o];
     int32_t* par = parent + base;
-    // each unordered pair once: only neighbours that precede this cell in row-major order
+    const int my_root = par[o];
     for (int dr = -r; dr <= 0; ++dr) {
         int yy = y + dr;
         if (yy < 0) continue;
         int dc_hi = dr == 0 ? -1 : r;
         for (int dc = -r; dc <= dc_hi; ++dc) {
+            if (dr >= -1 && dc >= -1 && dc <= 1) continue;  // pass 1 did these
             int xx = x + dc;
             if (xx < 0 || xx >= W) continue;
             int q = yy * W + xx;
-            if (state[base + q] == 2 && within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2))
-                uf_union(par, o, q);
+            if (state[base + q] != 2) continue;
+            if (par[q] == my_root) continue;  // a (possibly stale) common ancestor: already joined
+            if (within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2)) uf_union(par, o, q);
         }
     }
 }
@@ -298,52 +330,88 @@ int flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, int32_t*
 }
 
 // ---- cluster summaries ------------------------------------------------------------------------
-// acc: double [batch][max_clusters][8] = n, sum r, sum c, sum vx, sum vy, sum rr, sum rc, sum cc
+// Integer moments (n, sum r, sum c, sum rr, sum rc, sum cc) are accumulated exactly in uint64;
+// sum vx / sum vy in fp64.  Compact cells are in row-major order, so the lanes of a warp mostly
+// share a label: they are combined with match_any + shuffles and one lane per distinct label
+// issues the atomics.  acc: [batch][max_clusters][8] 64-bit words.
 __global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__ vx, const float* __restrict__ vy,
                                                        int H, int W, int cap, const int32_t* __restrict__ n_valid,
                                                        const int32_t* __restrict__ labels,
                                                        const int32_t* __restrict__ indices, int max_clusters,
-                                                       double* __restrict__ acc) {
+                                                       unsigned long long* __restrict__ acc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const int n = min(n_valid[b], cap);
-    if (i >= n) return;
-    const size_t o = static_cast<size_t>(b) * cap + i;
-    const int lab = labels[o];
-    if (lab < 0 || lab >= max_clusters) return;
-    const int r = indices[2 * o], c = indices[2 * o + 1];
-    const size_t p = (static_cast<size_t>(b) * H + r) * W + c;
-    double* a = acc + (static_cast<size_t>(b) * max_clusters + lab) * 8;
-    const double dr = r, dc = c;
-    atomicAdd(a + 0, 1.0);
-    atomicAdd(a + 1, dr);
-    atomicAdd(a + 2, dc);
-    atomicAdd(a + 3, static_cast<double>(vx[p]));
-    atomicAdd(a + 4, static_cast<double>(vy[p]));
-    atomicAdd(a + 5, dr * dr);
-    atomicAdd(a + 6, dr * dc);
-    atomicAdd(a + 7, dc * dc);
+    if (static_cast<int>(blockIdx.x * blockDim.x) >= n) return;  // whole CTA past the end
+    int lab = -1;
+    unsigned long long r = 0, c = 0;
+    double fvx = 0.0, fvy = 0.0;
+    if (i < n) {
+        const size_t o = static_cast<size_t>(b) * cap + i;
+        lab = labels[o];
+        if (lab >= max_clusters) lab = -1;
+        if (lab >= 0) {
+            r = indices[2 * o], c = indices[2 * o + 1];
+            const size_t p = (static_cast<size_t>(b) * H + r) * W + c;
+            fvx = vx[p], fvy = vy[p];
+        }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, lab);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    unsigned long long sr = 0, sc = 0, srr = 0, src = 0, scc = 0;
+    double svx = 0.0, svy = 0.0;
+    unsigned rem = peers;
+    while (__any_sync(0xffffffffu, rem != 0)) {
+        const int src_lane = rem ? __ffs(rem) - 1 : 0;
+        const unsigned long long tr = __shfl_sync(0xffffffffu, r, src_lane);
+        const unsigned long long tc = __shfl_sync(0xffffffffu, c, src_lane);
+        const double tvx = __shfl_sync(0xffffffffu, fvx, src_lane);
+        const double tvy = __shfl_sync(0xffffffffu, fvy, src_lane);
+        if (rem) {
+            sr += tr, sc += tc, srr += tr * tr, src += tr * tc, scc += tc * tc;
+            svx += tvx, svy += tvy;
+            rem &= rem - 1;
+        }
+    }
+    if (lane == leader && lab >= 0) {
+        unsigned long long* a = acc + (static_cast<size_t>(b) * max_clusters + lab) * 8;
+        atomicAdd(a + 0, static_cast<unsigned long long>(__popc(peers)));
+        atomicAdd(a + 1, sr);
+        atomicAdd(a + 2, sc);
+        atomicAdd(reinterpret_cast<double*>(a + 3), svx);
+        atomicAdd(reinterpret_cast<double*>(a + 4), svy);
+        atomicAdd(a + 5, srr);
+        atomicAdd(a + 6, src);
+        atomicAdd(a + 7, scc);
+    }
 }
 
-__global__ void __launch_bounds__(256) k_cluster_finalize(int total, double* __restrict__ acc) {
+// in place: 64-bit accumulators -> the 8 doubles of the summary
+__global__ void __launch_bounds__(256) k_cluster_finalize(int total, unsigned long long* __restrict__ acc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    double* a = acc + static_cast<size_t>(i) * 8;
-    const double n = a[0];
-    if (n <= 0) return;
-    const double mr = a[1] / n, mc = a[2] / n;
+    unsigned long long* a = acc + static_cast<size_t>(i) * 8;
+    double* d = reinterpret_cast<double*>(a);
+    const unsigned long long cnt = a[0];
+    if (cnt == 0) return;  // all-zero bits are also 0.0
+    const double n = static_cast<double>(cnt);
+    const double sr = static_cast<double>(a[1]), sc = static_cast<double>(a[2]);
+    const double srr = static_cast<double>(a[5]), src = static_cast<double>(a[6]), scc = static_cast<double>(a[7]);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    // row / col sums are exact integers in fp64, so the one-pass covariance is exact up to the final divisions
-    const double crr = n > 1 ? (a[5] - a[1] * a[1] / n) / (n - 1) : nan;
-    const double crc = n > 1 ? (a[6] - a[1] * a[2] / n) / (n - 1) : nan;
-    const double ccc = n > 1 ? (a[7] - a[2] * a[2] / n) / (n - 1) : nan;
-    a[1] = mr;
-    a[2] = mc;
-    a[3] = a[3] / n;
-    a[4] = a[4] / n;
-    a[5] = crr;
-    a[6] = crc;
-    a[7] = ccc;
+    const double mr = sr / n, mc = sc / n;
+    // np.cov (ddof 1) from exact integer moments
+    const double crr = cnt > 1 ? (srr - sr * sr / n) / (n - 1) : nan;
+    const double crc = cnt > 1 ? (src - sr * sc / n) / (n - 1) : nan;
+    const double ccc = cnt > 1 ? (scc - sc * sc / n) / (n - 1) : nan;
+    d[0] = n;
+    d[1] = mr;
+    d[2] = mc;
+    d[3] = d[3] / n;
+    d[4] = d[4] / n;
+    d[5] = crr;
+    d[6] = crc;
+    d[7] = ccc;
 }
 
 }  // namespace
@@ -385,9 +453,22 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, DATMO_TAG_DBSCAN);
-        k_union<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+        k_union_near<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
     }
     DATMO_POST_LAUNCH(h);
+    if (r > 1) {
+        dim3 gf(static_cast<unsigned>(ceil_div64(n, 256)), batch);
+        {
+            LaunchScope ls(h, DATMO_TAG_DBSCAN);
+            k_flatten<<<gf, 256, 0, h->stream>>>(state, n, parent, is_root);
+        }
+        DATMO_POST_LAUNCH(h);
+        {
+            LaunchScope ls(h, DATMO_TAG_DBSCAN);
+            k_union_far<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+        }
+        DATMO_POST_LAUNCH(h);
+    }
     {
         LaunchScope ls(h, DATMO_TAG_DBSCAN);
         dim3 gf(static_cast<unsigned>(ceil_div64(n, 256)), batch);
@@ -418,13 +499,13 @@ extern "C" int datmo_cluster_summary_dev(datmo_handle_t h, const float* vx_f, co
         LaunchScope ls(h, DATMO_TAG_CLUSTER);
         dim3 g(ceil_div(cap, 256), batch);
         k_cluster_accum<<<g, 256, 0, h->stream>>>(vx_f, vy_f, H, W, cap, n_valid, labels, indices, max_clusters,
-                                                  summary);
+                                                  reinterpret_cast<unsigned long long*>(summary));
     }
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, DATMO_TAG_CLUSTER);
-        k_cluster_finalize<<<ceil_div(static_cast<int>(total), 256), 256, 0, h->stream>>>(static_cast<int>(total),
-                                                                                          summary);
+        k_cluster_finalize<<<ceil_div(static_cast<int>(total), 256), 256, 0, h->stream>>>(
+            static_cast<int>(total), reinterpret_cast<unsigned long long*>(summary));
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;

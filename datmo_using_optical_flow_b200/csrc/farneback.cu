@@ -413,6 +413,9 @@ __global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict
 // direct (non-running) sums and solves the 2x2 system per pixel.
 // ------------------------------------------------------------------------------------
 constexpr int FI_TX = 32, FI_TY = 32, FI_THREADS = 256;
+#ifndef DATMO_FI_TILE_DEFAULT
+#define DATMO_FI_TILE_DEFAULT 1
+#endif
 
 __device__ __forceinline__ float2 solve_flow(const float g[5]) {
     // g = blurred (g11, g12, g22, h1, h2)
@@ -486,6 +489,124 @@ __global__ void __launch_bounds__(FI_THREADS) k_flow_iter(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------
+// F5 + F6 fused, specialised for a compile-time window (winsize 14 / 15 -> 15 taps).
+//
+// One shared-memory buffer, three in-place passes:
+//   1. M for the tile + halo (FUSED: gathered straight from R0 / R1 / flow);
+//   2. vertical window sums, one thread per (column, channel), van Herk / Gil-Werman:
+//      the column is cut into segments of WIN rows; a window that starts inside segment k
+//      is (suffix sum of segment k) + (prefix sum of segment k+1).  Every output is a sum
+//      of exactly its own window's values — no running-sum cancellation — at ~3 adds and
+//      ~1.5 shared loads per output instead of WIN of each.  The thread owns its column,
+//      so the sums overwrite the M values it has already consumed;
+//   3. horizontal window sums, one thread per (row, channel), same scheme along x;
+//   4. per-pixel 2x2 solve, float2 store.
+// ------------------------------------------------------------------------------------
+template <int WIN, int NOUT>
+__device__ __forceinline__ void window_sums_inplace(float* __restrict__ p, const int stride) {
+    constexpr int NIN = NOUT + WIN - 1;
+    float S[WIN];
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) S[j] = p[j * stride];
+#pragma unroll
+    for (int j = WIN - 2; j >= 0; --j) S[j] += S[j + 1];
+#pragma unroll
+    for (int base = 0; base < NOUT; base += WIN) {
+        p[base * stride] = S[0];
+        float P = 0.f;
+        float nxt[WIN];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) {
+            const int idx = base + WIN + j;
+            if (idx < NIN) {
+                const float v = p[idx * stride];
+                nxt[j] = v;
+                P += v;
+            } else {
+                nxt[j] = 0.f;
+            }
+            const int y = base + 1 + j;
+            if (j < WIN - 1 && y < NOUT) p[y * stride] = S[j + 1] + P;
+        }
+#pragma unroll
+        for (int j = WIN - 2; j >= 0; --j) nxt[j] += nxt[j + 1];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) S[j] = nxt[j];
+    }
+}
+
+template <int TX, int TY, int WIN>
+struct FlowTile {
+    static constexpr int M = WIN / 2;
+    static constexpr int RW = TX + 2 * M, RH = TY + 2 * M;
+    static constexpr int SW = RW | 1;  // odd row stride: column walks and row walks are both conflict-free
+    static constexpr int THREADS = 256;
+    static constexpr size_t SMEM = static_cast<size_t>(5) * RH * SW * sizeof(float);
+};
+
+template <int TX, int TY, int WIN, bool FUSED>
+__global__ void __launch_bounds__(256) k_flow_iter_w(const float* __restrict__ R0, const float* __restrict__ R1,
+                                                     const float2* __restrict__ flow_in,
+                                                     const float* __restrict__ Min, float2* __restrict__ flow_out,
+                                                     int w, int h, float norm) {
+    using T = FlowTile<TX, TY, WIN>;
+    constexpr int M = T::M, RW = T::RW, RH = T::RH, SW = T::SW, NT = T::THREADS;
+    extern __shared__ float sM[];  // [5][RH][SW]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, b = blockIdx.z;
+    const size_t plane = static_cast<size_t>(w) * h;
+    const float* R0b = R0 + static_cast<size_t>(b) * 5 * plane;
+    const float* R1b = R1 + static_cast<size_t>(b) * 5 * plane;
+    const float* Mb = Min + static_cast<size_t>(b) * 5 * plane;
+    const float2* fb = flow_in + static_cast<size_t>(b) * plane;
+    // pass 1: M over tile + halo; (yy, xx) advance incrementally, no division in the loop
+    {
+        int yy = tid / RW, xx = tid - yy * RW;
+        constexpr int DY = NT / RW, DX = NT - DY * RW;
+        for (; yy < RH;) {
+            const int gx = min(max(x0 - M + xx, 0), w - 1);
+            const int gy = min(max(y0 - M + yy, 0), h - 1);
+            float Mv[5];
+            if (FUSED) {
+                compute_M(R0b, R1b, plane, w, h, gx, gy, fb[static_cast<size_t>(gy) * w + gx], Mv);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) Mv[c] = Mb[c * plane + static_cast<size_t>(gy) * w + gx];
+            }
+#pragma unroll
+            for (int c = 0; c < 5; ++c) sM[(c * RH + yy) * SW + xx] = Mv[c];
+            yy += DY;
+            xx += DX;
+            if (xx >= RW) xx -= RW, ++yy;
+        }
+    }
+    __syncthreads();
+    // pass 2: vertical, thread per (channel, column)
+    for (int i = tid; i < 5 * RW; i += NT) {
+        const int c = i / RW, xx = i - c * RW;
+        window_sums_inplace<WIN, TY>(sM + c * RH * SW + xx, SW);
+    }
+    __syncthreads();
+    // pass 3: horizontal, thread per (channel, row); rows 0..TY-1 now hold the vertical sums
+    for (int i = tid; i < 5 * TY; i += NT) {
+        const int c = i / TY, y = i - c * TY;
+        window_sums_inplace<WIN, TX>(sM + (c * RH + y) * SW, 1);
+    }
+    __syncthreads();
+    // pass 4: solve
+    float2* fo = flow_out + static_cast<size_t>(b) * plane;
+    for (int i = tid; i < TX * TY; i += NT) {
+        const int y = i / TX, x = i - y * TX;
+        const int gx = x0 + x, gy = y0 + y;
+        if (gx >= w || gy >= h) continue;
+        float g[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) g[c] = sM[(c * RH + y) * SW + x] * norm;
+        fo[static_cast<size_t>(gy) * w + gx] = solve_flow(g);
+    }
+}
+
 size_t flow_iter_smem(int m) {
     int RW = FI_TX + 2 * m, RH = FI_TY + 2 * m, SW = RW | 1;
     return static_cast<size_t>(5) * (RH + FI_TY) * SW * sizeof(float);
@@ -534,10 +655,49 @@ int launch_polyexp(datmo_ctx* h, const float* I, float* R, int w, int hh, int B,
     return DATMO_OK;
 }
 
+int flow_tile_choice() {
+    const char* e = getenv("DATMO_FI_TILE");
+    return e ? atoi(e) : DATMO_FI_TILE_DEFAULT;
+}
+
+template <int TX, int TY, bool FUSED>
+int launch_flow_iter_w(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, const float* Min,
+                       float* flow_out, int w, int hh, int B, float norm) {
+    using T = FlowTile<TX, TY, 15>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter_w<TX, TY, 15, FUSED>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(T::SMEM)));
+        attr_set = true;
+    }
+    dim3 g(ceil_div(w, TX), ceil_div(hh, TY), B);
+    {
+        LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
+        k_flow_iter_w<TX, TY, 15, FUSED><<<g, T::THREADS, T::SMEM, h->stream>>>(
+            R0, R1, reinterpret_cast<const float2*>(flow_in), Min, reinterpret_cast<float2*>(flow_out), w, hh, norm);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
 template <bool FUSED>
 int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, const float* Min,
                      float* flow_out, int w, int hh, int B, int winsize) {
     int m = winsize / 2;
+    float norm = static_cast<float>(1.0 / (static_cast<double>(winsize) * winsize));
+    if (m == 7 && !getenv("DATMO_GENERIC_FLOW_ITER")) {
+        // the reference's winsize 15 (and 14): compile-time window, tile picked from a small table
+        static const int tile = flow_tile_choice();
+        switch (tile) {
+            case 1: return launch_flow_iter_w<64, 32, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 2: return launch_flow_iter_w<32, 64, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 3: return launch_flow_iter_w<64, 64, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 4: return launch_flow_iter_w<48, 48, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 5: return launch_flow_iter_w<96, 32, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            default: return launch_flow_iter_w<32, 32, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+        }
+    }
     size_t smem = flow_iter_smem(m);
     DATMO_REQUIRE(h, smem <= 227 * 1024, "winsize too large for the flow-iteration tile");
     static size_t configured = 0;
@@ -547,7 +707,6 @@ int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float
         configured = smem;
     }
     dim3 g(ceil_div(w, FI_TX), ceil_div(hh, FI_TY), B);
-    float norm = static_cast<float>(1.0 / (static_cast<double>(winsize) * winsize));
     {
         LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
         k_flow_iter<FUSED><<<g, FI_THREADS, smem, h->stream>>>(R0, R1, reinterpret_cast<const float2*>(flow_in), Min,
