@@ -13,6 +13,8 @@
 //   border cell   takes the smallest root among its core neighbours, else noise (-1)
 //   label         rank of the root among all roots in ascending order
 // Row-major ranks (the order of np.nonzero) come from a flag scan of the grid.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) k_scan_block_sums(int32_t* __restrict__ b
 // pass 3: exclusive rank of every flagged cell (others get -1)
 __global__ void __launch_bounds__(SCAN_THREADS) k_flag_ranks(const uint8_t* __restrict__ flags, int64_t n, int nblk,
                                                              const int32_t* __restrict__ block_offs,
-                                                             int32_t* __restrict__ rank) {
+                                                             int32_t* __restrict__ rank, int sparse) {
     const int blk = blockIdx.x, b = blockIdx.y;
     const uint8_t* f = flags + static_cast<size_t>(b) * n;
     int32_t* r = rank + static_cast<size_t>(b) * n;
@@ -111,7 +113,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_flag_ranks(const uint8_t* __re
     for (int i = 0; i < PER; ++i) {
         int64_t p = p0 + i;
         if (p < n) {
-            r[p] = local[i] ? run : -1;
+            // sparse: only flagged cells are ever looked up, skip the 4 B/cell fill
+            if (local[i])
+                r[p] = run;
+            else if (!sparse)
+                r[p] = -1;
             run += local[i];
         }
     }
@@ -141,7 +147,20 @@ __global__ void __launch_bounds__(256) k_core(const float* __restrict__ vx, cons
     uint8_t st = 0;
     if (valid[base + o]) {
         const float vx0 = vx[base + o], vy0 = vy[base + o];
-        int cnt = 0;
+        // nearest neighbours first: inside a moving region self + the 4-neighbourhood usually
+        // reaches min_samples; only otherwise count over the whole window
+        int cnt = 1;  // self
+        if (r >= 1 && cnt < min_samples) {
+            const int ndr[4] = {0, 0, -1, 1}, ndc[4] = {-1, 1, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int yy = y + ndr[k], xx = x + ndc[k];
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const size_t q = base + static_cast<size_t>(yy) * W + xx;
+                if (valid[q] && within_eps(ndr[k], ndc[k], vx0, vy0, vx[q], vy[q], eps2)) ++cnt;
+            }
+        }
+        if (cnt < min_samples) cnt = 0;  // inconclusive: recount exactly
         for (int dr = -r; dr <= r && cnt < min_samples; ++dr) {
             int yy = y + dr;
             if (yy < 0 || yy >= H) continue;
@@ -192,8 +211,42 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
     }
 }
 
-// Union pass 1: only the four preceding 8-neighbours.  In dense moving regions this
-// already joins almost every cell of a component with ~4 cheap links per cell.
+// Link pass 1 (no atomics): every core cell points at the smallest-index core cell among its
+// four preceding 8-neighbours that is within eps (or stays its own root).  All candidates
+// precede the cell in row-major order, so the result is a forest, and an 8-connected region
+// of mutually close cells collapses into ONE tree (diagonal chains end on its top row / left
+// column, which chain to its first cell).  Linking to the first cell of the whole half-window
+// instead was measured slower: its chains stride (-4,-2) and stay interleaved, leaving several
+// trees per region and defeating the quick reject of pass 2.
+__global__ void __launch_bounds__(256) k_link_near(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                   const uint8_t* __restrict__ state, int H, int W, int r,
+                                                   double eps2, int32_t* __restrict__ parent) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W || r < 1) return;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const int o = y * W + x;
+    if (state[base + o] != 2) return;
+    const float vx0 = vx[base + o], vy0 = vy[base + o];
+    int best = o;
+    // ascending index order: (-1,-1), (-1,0), (-1,+1), (0,-1); keep the first hit
+    const int ndr[4] = {-1, -1, -1, 0}, ndc[4] = {-1, 0, 1, -1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int yy = y + ndr[k], xx = x + ndc[k];
+        if (yy < 0 || xx < 0 || xx >= W) continue;
+        const int q = yy * W + xx;
+        if (q < best && state[base + q] == 2 &&
+            within_eps(ndr[k], ndc[k], vx0, vy0, vx[base + q], vy[base + q], eps2))
+            best = q;
+    }
+    parent[base + o] = best;
+}
+
+// Link pass 1b (after a flatten): the atomics-free pass leaves an 8-connected region split
+// into a few diagonal stripes (one per ragged top / left edge cell).  Join them: same four
+// neighbours, but now "same flattened parent" skips the pair, so only cells ON a stripe
+// interface reach the atomic path.  Afterwards trees == 8-connected regions of close cells.
 __global__ void __launch_bounds__(256) k_union_near(const float* __restrict__ vx, const float* __restrict__ vy,
                                                     const uint8_t* __restrict__ state, int H, int W, int r,
                                                     double eps2, int32_t* __restrict__ parent) {
@@ -203,47 +256,83 @@ __global__ void __launch_bounds__(256) k_union_near(const float* __restrict__ vx
     const size_t base = static_cast<size_t>(b) * H * W;
     const int o = y * W + x;
     if (state[base + o] != 2) return;
-    const float vx0 = vx[base + o], vy0 = vy[base + o];
     int32_t* par = parent + base;
-    const int ndr[4] = {0, -1, -1, -1}, ndc[4] = {-1, -1, 0, 1};
+    const int my_root = par[o];
+    int joined = -1;
+    const float vx0 = vx[base + o], vy0 = vy[base + o];
+    const int ndr[4] = {-1, -1, -1, 0}, ndc[4] = {-1, 0, 1, -1};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int yy = y + ndr[k], xx = x + ndc[k];
         if (yy < 0 || xx < 0 || xx >= W) continue;
         const int q = yy * W + xx;
-        if (state[base + q] == 2 && within_eps(ndr[k], ndc[k], vx0, vy0, vx[base + q], vy[base + q], eps2))
+        const int pq = par[q];
+        if (pq < 0 || pq == my_root || pq == joined) continue;
+        if (within_eps(ndr[k], ndc[k], vx0, vy0, vx[base + q], vy[base + q], eps2)) {
             uf_union(par, o, q);
+            joined = pq;
+        }
     }
 }
 
-// Union pass 2 (after a flatten): the rest of the preceding half-window.  parent[] now
-// holds each cell's pass-1 root, so "same parent" proves "same component" from one
-// cached load and skips both the fp64 distance test and the union; only the few pairs
-// that bridge different pass-1 components reach the atomic path.
+// Link pass 2 (after a flatten): the whole preceding half-window.  parent[] now holds each
+// cell's pass-1 root, so "same parent" proves "same component" from one cached load and
+// skips both the fp64 distance test and the union; only the few pairs that bridge different
+// pass-1 trees reach the atomic path.
 __global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx, const float* __restrict__ vy,
                                                    const uint8_t* __restrict__ state, int H, int W, int r,
                                                    double eps2, int32_t* __restrict__ parent) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
     const size_t base = static_cast<size_t>(b) * H * W;
-    const int o = y * W + x;
-    if (state[base + o] != 2) return;
-    const float vx0 = vx[base + o], vy0 = vy[base + o];
     int32_t* par = parent + base;
+    const int o = y * W + x;
+    const bool core = x < W && state[base + o] == 2;
+    if (!__any_sync(0xffffffffu, core)) return;  // three warps in four hold no core cell at all
+    // Warp-level quick reject.  The 32 cells of a warp share the footprint rows y-r..y,
+    // columns x0-r..x0+31+r.  If every core cell in that footprint already has the same
+    // pass-1 root there is nothing to join and the whole warp leaves after ~2(r+1) loads per
+    // lane instead of walking (r+1)(2r+1) neighbours each.
+    {
+        const int lane = threadIdx.x & 31;
+        const int xw0 = x - lane;  // first column of this warp
+        int lo = 0x7fffffff, hi = -1;
+        for (int dr = -r; dr <= 0; ++dr) {
+            const int yy = y + dr;
+            if (yy < 0) continue;
+            const int32_t* prow = par + yy * W;
+            for (int cx = xw0 - r + lane; cx <= xw0 + 31 + r; cx += 32) {
+                if (cx < 0 || cx >= W) continue;
+                const int p = prow[cx];
+                if (p >= 0) {
+                    lo = min(lo, p);
+                    hi = max(hi, p);
+                }
+            }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (hi < 0 || lo == hi) return;
+    }
+    if (!core) return;
+    const float vx0 = vx[base + o], vy0 = vy[base + o];
     const int my_root = par[o];
+    int joined = -1;  // the last foreign pass-1 tree this cell has already been united with
     for (int dr = -r; dr <= 0; ++dr) {
-        int yy = y + dr;
+        const int yy = y + dr;
         if (yy < 0) continue;
-        int dc_hi = dr == 0 ? -1 : r;
-        for (int dc = -r; dc <= dc_hi; ++dc) {
-            if (dr >= -1 && dc >= -1 && dc <= 1) continue;  // pass 1 did these
-            int xx = x + dc;
-            if (xx < 0 || xx >= W) continue;
-            int q = yy * W + xx;
-            if (state[base + q] != 2) continue;
-            if (par[q] == my_root) continue;  // a (possibly stale) common ancestor: already joined
-            if (within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2)) uf_union(par, o, q);
+        const int dc_lo = max(-r, -x), dc_hi = dr == 0 ? -1 : min(r, W - 1 - x);
+        const int32_t* prow = par + yy * W + x;
+        for (int dc = dc_lo; dc <= dc_hi; ++dc) {
+            // parent is -1 for anything that is not a core cell, so one load filters
+            // "not core", "same pass-1 tree" and "tree already joined"
+            const int pq = prow[dc];
+            if (pq < 0 || pq == my_root || pq == joined) continue;
+            const int q = yy * W + x + dc;
+            if (within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2)) {
+                uf_union(par, o, q);
+                joined = pq;
+            }
         }
     }
 }
@@ -307,8 +396,14 @@ __global__ void __launch_bounds__(256) k_labels(const float* __restrict__ vx, co
     indices[2 * out + 1] = x;
 }
 
+static int dbg_tag(int sub) {
+    // DATMO_DBSCAN_SUBTAGS=1 spreads the DBSCAN kernels over the other profiler tags (tools/dbscan_prof.py)
+    static const bool on = getenv("DATMO_DBSCAN_SUBTAGS") != nullptr;
+    return on ? sub : DATMO_TAG_DBSCAN;
+}
+
 int flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, int32_t* block_sums, int32_t* totals,
-              int32_t* rank, int tag) {
+              int32_t* rank, int tag, int sparse) {
     int nblk = static_cast<int>(ceil_div64(n, SCAN_ITEMS));
     dim3 g(nblk, batch);
     {
@@ -323,7 +418,7 @@ int flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, int32_t*
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, tag);
-        k_flag_ranks<<<g, SCAN_THREADS, 0, h->stream>>>(flags, n, nblk, block_sums, rank);
+        k_flag_ranks<<<g, SCAN_THREADS, 0, h->stream>>>(flags, n, nblk, block_sums, rank, sparse);
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
@@ -444,41 +539,52 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
         total = bump.off;
         if (!pass) DATMO_TRY(datmo_ws_reserve(h, total));
     }
-    DATMO_TRY(flag_scan(h, valid, n, batch, bsum, n_valid, rank, DATMO_TAG_DBSCAN));
+    DATMO_TRY(flag_scan(h, valid, n, batch, bsum, n_valid, rank, dbg_tag(0), 1));
     dim3 g(ceil_div(W, 256), H, batch);
     {
-        LaunchScope ls(h, DATMO_TAG_DBSCAN);
+        LaunchScope ls(h, dbg_tag(1));
         k_core<<<g, 256, 0, h->stream>>>(vx_f, vy_f, valid, H, W, r, eps2, min_samples, state, parent);
     }
     DATMO_POST_LAUNCH(h);
-    {
-        LaunchScope ls(h, DATMO_TAG_DBSCAN);
-        k_union_near<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
-    }
-    DATMO_POST_LAUNCH(h);
-    if (r > 1) {
-        dim3 gf(static_cast<unsigned>(ceil_div64(n, 256)), batch);
+    dim3 gf(static_cast<unsigned>(ceil_div64(n, 256)), batch);
+    if (r >= 1) {
         {
-            LaunchScope ls(h, DATMO_TAG_DBSCAN);
+            LaunchScope ls(h, dbg_tag(2));
+            k_link_near<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+        }
+        DATMO_POST_LAUNCH(h);
+        {
+            LaunchScope ls(h, dbg_tag(3));
             k_flatten<<<gf, 256, 0, h->stream>>>(state, n, parent, is_root);
         }
         DATMO_POST_LAUNCH(h);
         {
-            LaunchScope ls(h, DATMO_TAG_DBSCAN);
-            k_union_far<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+            LaunchScope ls(h, dbg_tag(5));
+            k_union_near<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
         }
         DATMO_POST_LAUNCH(h);
+        if (r > 1) {
+            {
+                LaunchScope ls(h, dbg_tag(3));
+                k_flatten<<<gf, 256, 0, h->stream>>>(state, n, parent, is_root);
+            }
+            DATMO_POST_LAUNCH(h);
+            {
+                LaunchScope ls(h, dbg_tag(4));
+                k_union_far<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+            }
+            DATMO_POST_LAUNCH(h);
+        }
     }
     {
-        LaunchScope ls(h, DATMO_TAG_DBSCAN);
-        dim3 gf(static_cast<unsigned>(ceil_div64(n, 256)), batch);
+        LaunchScope ls(h, dbg_tag(3));
         k_flatten<<<gf, 256, 0, h->stream>>>(state, n, parent, is_root);
     }
     DATMO_POST_LAUNCH(h);
     int32_t* ncl_out = n_clusters ? n_clusters : ncl;
-    DATMO_TRY(flag_scan(h, is_root, n, batch, bsum, ncl_out, root_rank, DATMO_TAG_DBSCAN));
+    DATMO_TRY(flag_scan(h, is_root, n, batch, bsum, ncl_out, root_rank, dbg_tag(0), 1));
     {
-        LaunchScope ls(h, DATMO_TAG_DBSCAN);
+        LaunchScope ls(h, dbg_tag(6));
         k_labels<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, parent, rank, root_rank, H, W, r, eps2, cap, labels,
                                            indices);
     }

@@ -310,6 +310,129 @@ __global__ void __launch_bounds__(PE_THREADS) k_polyexp(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------
+// F2 + F4 fused for the finest layer (scale 1): the pyramid image there is just the fixed
+// [1 2 1]/4 blur of the frame (REFLECT_101), so blur and polynomial expansion run in one
+// kernel straight from the uint8 / f32 frame; T and I never touch global memory.
+// Register-blocked: a thread produces 4 vertically adjacent r-values, then 4 horizontally
+// adjacent outputs (shared loads as float4), with the tap count a compile-time constant.
+// ------------------------------------------------------------------------------------
+constexpr int P0_TX = 64, P0_TY = 16, P0_THREADS = 256;
+
+template <typename SrcT, int N>
+__global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp(const SrcT* __restrict__ src, float* __restrict__ R,
+                                                             int w, int h, PolyCoef pc) {
+    constexpr int RW = P0_TX + 2 * N, RH = P0_TY + 2 * N;  // blurred-image region
+    constexpr int SWS = RW + 2, SHS = RH + 2;              // raw frame region (one more pixel each side)
+    constexpr int RWP = (RW + 3) & ~3;                     // r-array row stride, float4-aligned
+    __shared__ float sS[SHS * SWS];
+    __shared__ float sI[RH * RW];
+    __shared__ __align__(16) float sr[3][P0_TY * RWP];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * P0_TX, y0 = blockIdx.y * P0_TY, b = blockIdx.z;
+    const size_t plane = static_cast<size_t>(w) * h;
+    const SrcT* sb = src + b * plane;
+    // raw frame, reflected at the image border
+    for (int i = tid; i < SHS * SWS; i += P0_THREADS) {
+        const int yy = i / SWS, xx = i - yy * SWS;
+        const int gy = reflect101(y0 - N - 1 + yy, h), gx = reflect101(x0 - N - 1 + xx, w);
+        sS[i] = load_px(sb + static_cast<size_t>(gy) * w + gx);
+    }
+    __syncthreads();
+    // blurred image at replicate-clamped coordinates (what polyExp's border handling reads)
+    for (int i = tid; i < RH * RW; i += P0_THREADS) {
+        const int yy = i / RW, xx = i - yy * RW;
+        const int gy = min(max(y0 - N + yy, 0), h - 1), gx = min(max(x0 - N + xx, 0), w - 1);
+        const float* c = sS + (gy - (y0 - N - 1)) * SWS + (gx - (x0 - N - 1));
+        // rows first (f32), then columns, like the separable filter
+        const float t0 = 0.25f * c[-SWS - 1] + 0.5f * c[-SWS] + 0.25f * c[-SWS + 1];
+        const float t1 = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
+        const float t2 = 0.25f * c[SWS - 1] + 0.5f * c[SWS] + 0.25f * c[SWS + 1];
+        sI[i] = 0.25f * t0 + 0.5f * t1 + 0.25f * t2;
+    }
+    __syncthreads();
+    // vertical pass: 4 output rows per item
+    for (int i = tid; i < (P0_TY / 4) * RW; i += P0_THREADS) {
+        const int g = i / RW, xx = i - g * RW;
+        float v[4 + 2 * N];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; ++j) v[j] = sI[(g * 4 + j) * RW + xx];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float r0 = v[o + N] * pc.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float s0 = v[o + N - k], s1 = v[o + N + k];
+                const float p = s0 + s1;
+                r0 = fmaf(pc.g[k], p, r0);
+                r1 = fmaf(pc.xg[k], s1 - s0, r1);
+                r2 = fmaf(pc.xxg[k], p, r2);
+            }
+            const int a = (g * 4 + o) * RWP + xx;
+            sr[0][a] = r0;
+            sr[1][a] = r1;
+            sr[2][a] = r2;
+        }
+    }
+    __syncthreads();
+    // horizontal pass: 4 outputs per thread
+    float* Rb = R + static_cast<size_t>(b) * 5 * plane;
+    for (int i = tid; i < P0_TY * (P0_TX / 4); i += P0_THREADS) {
+        const int ty = i / (P0_TX / 4), tx = (i - ty * (P0_TX / 4)) * 4;
+        const int gy = y0 + ty, gx = x0 + tx;
+        if (gy >= h || gx >= w) continue;
+        constexpr int NV = ((4 + 2 * N) + 3) & ~3;
+        float a0[NV], a1[NV], a2[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j += 4) {
+            *reinterpret_cast<float4*>(a0 + j) = *reinterpret_cast<const float4*>(&sr[0][ty * RWP + tx + j]);
+            *reinterpret_cast<float4*>(a1 + j) = *reinterpret_cast<const float4*>(&sr[1][ty * RWP + tx + j]);
+            *reinterpret_cast<float4*>(a2 + j) = *reinterpret_cast<const float4*>(&sr[2][ty * RWP + tx + j]);
+        }
+        float o0[4], o1[4], o2[4], o3[4], o4[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int c = o + N;
+            float b1 = a0[c] * pc.g[0], b3 = a1[c] * pc.g[0], b5 = a2[c] * pc.g[0];
+            float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float tg = a0[c + k] + a0[c - k];
+                b1 = fmaf(tg, pc.g[k], b1);
+                b4 = fmaf(tg, pc.xxg[k], b4);
+                b2 = fmaf(a0[c + k] - a0[c - k], pc.xg[k], b2);
+                b3 = fmaf(a1[c + k] + a1[c - k], pc.g[k], b3);
+                b6 = fmaf(a1[c + k] - a1[c - k], pc.xg[k], b6);
+                b5 = fmaf(a2[c + k] + a2[c - k], pc.g[k], b5);
+            }
+            o0[o] = b3 * pc.ig11;
+            o1[o] = b2 * pc.ig11;
+            o2[o] = fmaf(b1, pc.ig03, b5 * pc.ig33);
+            o3[o] = fmaf(b1, pc.ig03, b4 * pc.ig33);
+            o4[o] = b6 * pc.ig55;
+        }
+        const size_t off = static_cast<size_t>(gy) * w + gx;
+        if ((w & 3) == 0 && gx + 3 < w) {
+            *reinterpret_cast<float4*>(Rb + off) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+            *reinterpret_cast<float4*>(Rb + plane + off) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+            *reinterpret_cast<float4*>(Rb + 2 * plane + off) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+            *reinterpret_cast<float4*>(Rb + 3 * plane + off) = make_float4(o3[0], o3[1], o3[2], o3[3]);
+            *reinterpret_cast<float4*>(Rb + 4 * plane + off) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                if (gx + o < w) {
+                    Rb[off + o] = o0[o];
+                    Rb[plane + off + o] = o1[o];
+                    Rb[2 * plane + off + o] = o2[o];
+                    Rb[3 * plane + off + o] = o3[o];
+                    Rb[4 * plane + off + o] = o4[o];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // F3: flow initialisation of a finer layer = bilinear resize of the coarser flow * mul
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_upsample_flow(const float2* __restrict__ fin, float2* __restrict__ fout,
@@ -341,42 +464,68 @@ __global__ void __launch_bounds__(128) k_upsample_flow(const float2* __restrict_
 // ------------------------------------------------------------------------------------
 __constant__ float c_border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
 
-__device__ __forceinline__ void compute_M(const float* __restrict__ R0, const float* __restrict__ R1, size_t plane,
-                                          int w, int h, int x, int y, float2 f, float M[5]) {
-    const float dx = f.x, dy = f.y;
-    float fx = static_cast<float>(x) + dx, fy = static_cast<float>(y) + dy;
+// Split in two so a caller can issue the loads of several pixels before consuming any
+// (the gathers are the long-latency part of a flow iteration).
+struct MTaps {
+    float q[5];      // R0 at the pixel
+    float t[5][4];   // R1 at the four bilinear taps, per channel
+    float a00, a01, a10, a11;
+    float dx, dy;
+    bool inside;
+};
+
+__device__ __forceinline__ void m_gather(const float* __restrict__ R0, const float* __restrict__ R1, size_t plane,
+                                         int w, int h, int x, int y, float2 f, MTaps& T) {
+    T.dx = f.x;
+    T.dy = f.y;
+    float fx = static_cast<float>(x) + f.x, fy = static_cast<float>(y) + f.y;
     const float x1f = floorf(fx), y1f = floorf(fy);
     fx -= x1f;
     fy -= y1f;
     const size_t o = static_cast<size_t>(y) * w + x;
-    const float q0 = R0[o], q1 = R0[plane + o], q2 = R0[2 * plane + o], q3 = R0[3 * plane + o],
-                q4 = R0[4 * plane + o];
-    float r2, r3, r4, r5, r6;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) T.q[c] = R0[c * plane + o];
     // float-domain test also rejects NaN / huge displacements
-    if (x1f >= 0.f && x1f < static_cast<float>(w - 1) && y1f >= 0.f && y1f < static_cast<float>(h - 1)) {
+    T.inside = x1f >= 0.f && x1f < static_cast<float>(w - 1) && y1f >= 0.f && y1f < static_cast<float>(h - 1);
+    if (T.inside) {
         const int x1 = static_cast<int>(x1f), y1 = static_cast<int>(y1f);
-        const float a01 = fx * (1.f - fy), a11 = fx * fy;
-        const float a00 = (1.f - fx) * (1.f - fy), a10 = (1.f - fx) * fy;
+        T.a01 = fx * (1.f - fy);
+        T.a11 = fx * fy;
+        T.a00 = (1.f - fx) * (1.f - fy);
+        T.a10 = (1.f - fx) * fy;
         const float* p = R1 + static_cast<size_t>(y1) * w + x1;
-        float s[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
             const float* pc = p + c * plane;
-            s[c] = a00 * pc[0] + a01 * pc[1] + a10 * pc[w] + a11 * pc[w + 1];
+            T.t[c][0] = pc[0];
+            T.t[c][1] = pc[1];
+            T.t[c][2] = pc[w];
+            T.t[c][3] = pc[w + 1];
         }
+    }
+}
+
+__device__ __forceinline__ void m_finish(const MTaps& T, int w, int h, int x, int y, float M[5]) {
+    const float dx = T.dx, dy = T.dy;
+    float r2, r3, r4, r5, r6;
+    if (T.inside) {
+        float s[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+            s[c] = T.a00 * T.t[c][0] + T.a01 * T.t[c][1] + T.a10 * T.t[c][2] + T.a11 * T.t[c][3];
         r2 = s[0];
         r3 = s[1];
-        r4 = (q2 + s[2]) * 0.5f;
-        r5 = (q3 + s[3]) * 0.5f;
-        r6 = (q4 + s[4]) * 0.25f;
+        r4 = (T.q[2] + s[2]) * 0.5f;
+        r5 = (T.q[3] + s[3]) * 0.5f;
+        r6 = (T.q[4] + s[4]) * 0.25f;
     } else {
         r2 = r3 = 0.f;
-        r4 = q2;
-        r5 = q3;
-        r6 = q4 * 0.5f;
+        r4 = T.q[2];
+        r5 = T.q[3];
+        r6 = T.q[4] * 0.5f;
     }
-    r2 = (q0 - r2) * 0.5f;
-    r3 = (q1 - r3) * 0.5f;
+    r2 = (T.q[0] - r2) * 0.5f;
+    r3 = (T.q[1] - r3) * 0.5f;
     r2 += r4 * dy + r6 * dx;
     r3 += r6 * dy + r5 * dx;
     if (x < 5 || x >= w - 5 || y < 5 || y >= h - 5) {
@@ -389,6 +538,13 @@ __device__ __forceinline__ void compute_M(const float* __restrict__ R0, const fl
     M[2] = r5 * r5 + r6 * r6;
     M[3] = r4 * r2 + r6 * r3;
     M[4] = r6 * r2 + r5 * r3;
+}
+
+__device__ __forceinline__ void compute_M(const float* __restrict__ R0, const float* __restrict__ R1, size_t plane,
+                                          int w, int h, int x, int y, float2 f, float M[5]) {
+    MTaps T;
+    m_gather(R0, R1, plane, w, h, x, y, f, T);
+    m_finish(T, w, h, x, y, M);
 }
 
 __global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict__ R0, const float* __restrict__ R1,
@@ -414,7 +570,7 @@ __global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict
 // ------------------------------------------------------------------------------------
 constexpr int FI_TX = 32, FI_TY = 32, FI_THREADS = 256;
 #ifndef DATMO_FI_TILE_DEFAULT
-#define DATMO_FI_TILE_DEFAULT 1
+#define DATMO_FI_TILE_DEFAULT 3
 #endif
 
 __device__ __forceinline__ float2 solve_flow(const float g[5]) {
@@ -536,22 +692,22 @@ __device__ __forceinline__ void window_sums_inplace(float* __restrict__ p, const
     }
 }
 
-template <int TX, int TY, int WIN>
+template <int TX, int TY, int WIN, int NT_>
 struct FlowTile {
     static constexpr int M = WIN / 2;
     static constexpr int RW = TX + 2 * M, RH = TY + 2 * M;
     static constexpr int SW = RW | 1;  // odd row stride: column walks and row walks are both conflict-free
-    static constexpr int THREADS = 256;
+    static constexpr int THREADS = NT_;
     static constexpr size_t SMEM = static_cast<size_t>(5) * RH * SW * sizeof(float);
 };
 
-template <int TX, int TY, int WIN, bool FUSED>
-__global__ void __launch_bounds__(256) k_flow_iter_w(const float* __restrict__ R0, const float* __restrict__ R1,
-                                                     const float2* __restrict__ flow_in,
-                                                     const float* __restrict__ Min, float2* __restrict__ flow_out,
-                                                     int w, int h, float norm) {
-    using T = FlowTile<TX, TY, WIN>;
-    constexpr int M = T::M, RW = T::RW, RH = T::RH, SW = T::SW, NT = T::THREADS;
+template <int TX, int TY, int WIN, int NT, int MINB, bool FUSED>
+__global__ void __launch_bounds__(NT, MINB) k_flow_iter_w(const float* __restrict__ R0, const float* __restrict__ R1,
+                                                    const float2* __restrict__ flow_in,
+                                                    const float* __restrict__ Min, float2* __restrict__ flow_out,
+                                                    int w, int h, float norm) {
+    using T = FlowTile<TX, TY, WIN, NT>;
+    constexpr int M = T::M, RW = T::RW, RH = T::RH, SW = T::SW;
     extern __shared__ float sM[];  // [5][RH][SW]
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, b = blockIdx.z;
@@ -560,25 +716,60 @@ __global__ void __launch_bounds__(256) k_flow_iter_w(const float* __restrict__ R
     const float* R1b = R1 + static_cast<size_t>(b) * 5 * plane;
     const float* Mb = Min + static_cast<size_t>(b) * 5 * plane;
     const float2* fb = flow_in + static_cast<size_t>(b) * plane;
-    // pass 1: M over tile + halo; (yy, xx) advance incrementally, no division in the loop
+    // pass 1: M over tile + halo, two pixels per trip: the flow of the NEXT trip is
+    // prefetched, and both pixels' gathers are issued before either is consumed.
     {
-        int yy = tid / RW, xx = tid - yy * RW;
-        constexpr int DY = NT / RW, DX = NT - DY * RW;
-        for (; yy < RH;) {
-            const int gx = min(max(x0 - M + xx, 0), w - 1);
-            const int gy = min(max(y0 - M + yy, 0), h - 1);
-            float Mv[5];
-            if (FUSED) {
-                compute_M(R0b, R1b, plane, w, h, gx, gy, fb[static_cast<size_t>(gy) * w + gx], Mv);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 5; ++c) Mv[c] = Mb[c * plane + static_cast<size_t>(gy) * w + gx];
+        constexpr int NPIX = RW * RH;
+        auto locate = [&](int i, int& gx, int& gy, int& so) {
+            const int yy = i / RW, xx = i - yy * RW;  // RW is a compile-time constant
+            gx = min(max(x0 - M + xx, 0), w - 1);
+            gy = min(max(y0 - M + yy, 0), h - 1);
+            so = yy * SW + xx;
+        };
+        if (FUSED) {
+            int gxa, gya, soa, gxb, gyb, sob;
+            float2 fa = make_float2(0.f, 0.f), fbv = fa;
+            int ia = tid, ib = tid + NT;
+            if (ia < NPIX) {
+                locate(ia, gxa, gya, soa);
+                fa = fb[static_cast<size_t>(gya) * w + gxa];
             }
+            if (ib < NPIX) {
+                locate(ib, gxb, gyb, sob);
+                fbv = fb[static_cast<size_t>(gyb) * w + gxb];
+            }
+            for (; ia < NPIX; ia += 2 * NT, ib += 2 * NT) {
+                const bool has_b = ib < NPIX;
+                MTaps Ta, Tb;
+                m_gather(R0b, R1b, plane, w, h, gxa, gya, fa, Ta);
+                if (has_b) m_gather(R0b, R1b, plane, w, h, gxb, gyb, fbv, Tb);
+                // prefetch the next trip's flow while these gathers are in flight
+                const int cgxa = gxa, cgya = gya, csoa = soa, cgxb = gxb, cgyb = gyb, csob = sob;
+                if (ia + 2 * NT < NPIX) {
+                    locate(ia + 2 * NT, gxa, gya, soa);
+                    fa = fb[static_cast<size_t>(gya) * w + gxa];
+                }
+                if (ib + 2 * NT < NPIX) {
+                    locate(ib + 2 * NT, gxb, gyb, sob);
+                    fbv = fb[static_cast<size_t>(gyb) * w + gxb];
+                }
+                float Mv[5];
+                m_finish(Ta, w, h, cgxa, cgya, Mv);
 #pragma unroll
-            for (int c = 0; c < 5; ++c) sM[(c * RH + yy) * SW + xx] = Mv[c];
-            yy += DY;
-            xx += DX;
-            if (xx >= RW) xx -= RW, ++yy;
+                for (int c = 0; c < 5; ++c) sM[c * RH * SW + csoa] = Mv[c];
+                if (has_b) {
+                    m_finish(Tb, w, h, cgxb, cgyb, Mv);
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) sM[c * RH * SW + csob] = Mv[c];
+                }
+            }
+        } else {
+            for (int i = tid; i < NPIX; i += NT) {
+                int gx, gy, so;
+                locate(i, gx, gy, so);
+#pragma unroll
+                for (int c = 0; c < 5; ++c) sM[c * RH * SW + so] = Mb[c * plane + static_cast<size_t>(gy) * w + gx];
+            }
         }
     }
     __syncthreads();
@@ -660,13 +851,36 @@ int flow_tile_choice() {
     return e ? atoi(e) : DATMO_FI_TILE_DEFAULT;
 }
 
-template <int TX, int TY, bool FUSED>
+// finest layer: fused blur + polyexp when the tap count has a compile-time instance
+bool pyr0_polyexp_supported(int poly_n) { return (poly_n == 5 || poly_n == 7) && !getenv("DATMO_NO_PYR0_FUSION"); }
+
+int launch_pyr0_polyexp(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, float* R, const PolyCoef& pc) {
+    dim3 g(ceil_div(W, P0_TX), ceil_div(H, P0_TY), B);
+    {
+        LaunchScope ls(h, DATMO_TAG_POLYEXP);
+        if (dtype == DATMO_U8) {
+            if (pc.n == 5)
+                k_pyr0_polyexp<uint8_t, 5><<<g, P0_THREADS, 0, h->stream>>>(static_cast<const uint8_t*>(img), R, W, H, pc);
+            else
+                k_pyr0_polyexp<uint8_t, 7><<<g, P0_THREADS, 0, h->stream>>>(static_cast<const uint8_t*>(img), R, W, H, pc);
+        } else {
+            if (pc.n == 5)
+                k_pyr0_polyexp<float, 5><<<g, P0_THREADS, 0, h->stream>>>(static_cast<const float*>(img), R, W, H, pc);
+            else
+                k_pyr0_polyexp<float, 7><<<g, P0_THREADS, 0, h->stream>>>(static_cast<const float*>(img), R, W, H, pc);
+        }
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+template <int TX, int TY, int NT, int MINB, bool FUSED>
 int launch_flow_iter_w(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, const float* Min,
                        float* flow_out, int w, int hh, int B, float norm) {
-    using T = FlowTile<TX, TY, 15>;
+    using T = FlowTile<TX, TY, 15, NT>;
     static bool attr_set = false;
     if (!attr_set) {
-        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter_w<TX, TY, 15, FUSED>,
+        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter_w<TX, TY, 15, NT, MINB, FUSED>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  static_cast<int>(T::SMEM)));
         attr_set = true;
@@ -674,7 +888,7 @@ int launch_flow_iter_w(datmo_ctx* h, const float* R0, const float* R1, const flo
     dim3 g(ceil_div(w, TX), ceil_div(hh, TY), B);
     {
         LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
-        k_flow_iter_w<TX, TY, 15, FUSED><<<g, T::THREADS, T::SMEM, h->stream>>>(
+        k_flow_iter_w<TX, TY, 15, NT, MINB, FUSED><<<g, T::THREADS, T::SMEM, h->stream>>>(
             R0, R1, reinterpret_cast<const float2*>(flow_in), Min, reinterpret_cast<float2*>(flow_out), w, hh, norm);
     }
     DATMO_POST_LAUNCH(h);
@@ -690,12 +904,15 @@ int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float
         // the reference's winsize 15 (and 14): compile-time window, tile picked from a small table
         static const int tile = flow_tile_choice();
         switch (tile) {
-            case 1: return launch_flow_iter_w<64, 32, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 2: return launch_flow_iter_w<32, 64, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 3: return launch_flow_iter_w<64, 64, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 4: return launch_flow_iter_w<48, 48, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 5: return launch_flow_iter_w<96, 32, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            default: return launch_flow_iter_w<32, 32, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 0: return launch_flow_iter_w<32, 32, 256, 4, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 2: return launch_flow_iter_w<64, 32, 512, 1, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 3: return launch_flow_iter_w<64, 32, 256, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 4: return launch_flow_iter_w<64, 16, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 5: return launch_flow_iter_w<128, 16, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 6: return launch_flow_iter_w<64, 32, 384, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 7: return launch_flow_iter_w<64, 32, 512, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 8: return launch_flow_iter_w<32, 32, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            default: return launch_flow_iter_w<64, 32, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
         }
     }
     size_t smem = flow_iter_smem(m);
@@ -787,9 +1004,14 @@ int fb_run_chunk(datmo_ctx* h, const void* prev, const void* next, int dtype, in
         float* I1 = ws.I + B * n;
         float* R0 = ws.R;
         float* R1 = ws.R + B * 5 * n;
-        DATMO_TRY(launch_pyr(h, prev, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I0));
-        DATMO_TRY(launch_pyr(h, next, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I1));
-        DATMO_TRY(launch_polyexp(h, ws.I, ws.R, L.w, L.h, 2 * B, pc));
+        if (L.k == 0 && L.w == W && L.h == H && pyr0_polyexp_supported(pc.n)) {
+            DATMO_TRY(launch_pyr0_polyexp(h, prev, dtype, H, W, B, R0, pc));
+            DATMO_TRY(launch_pyr0_polyexp(h, next, dtype, H, W, B, R1, pc));
+        } else {
+            DATMO_TRY(launch_pyr(h, prev, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I0));
+            DATMO_TRY(launch_pyr(h, next, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I1));
+            DATMO_TRY(launch_polyexp(h, ws.I, ws.R, L.w, L.h, 2 * B, pc));
+        }
         float* fin;
         float* fout;
         if (cur == nullptr) {

@@ -371,3 +371,91 @@ def default_engine(device: int | None = None) -> Engine:
     if dev not in _default:
         _default[dev] = Engine(dev)
     return _default[dev]
+
+
+class HostFlowPipeline:
+    """Host-buffer entry to the flow -> clusters chain for a stream of frame-pair batches.
+
+    Pinned host uint8 pairs go in, host arrays come out (counts, labels, indices, cluster
+    summaries — what the reference's driver loop consumes after main.py:577-615).  Copies
+    run on their own streams and are double-buffered against the compute stream, so batch
+    i+1 is uploading / computing while batch i is read back; every copy still happens for
+    every batch.  Usage: ``submit(slot, prev, nxt)`` then ``collect(slot)``; keep at most
+    ``n_slots`` submissions outstanding.
+    """
+
+    def __init__(self, eng: Engine, batch: int, H: int, W: int, px_x: float, px_y: float, alpha_cont: float,
+                 eps: float, min_samples: int, params=None, cap: int | None = None, max_clusters: int = 1024,
+                 n_slots: int = 2):
+        self.eng, self.B, self.H, self.W = eng, batch, H, W
+        self.args = (px_x, px_y, alpha_cont, eps, min_samples)
+        self.params = params or farneback_params()
+        self.cap = H * W if cap is None else cap
+        self.max_clusters = max_clusters
+        with torch.cuda.device(eng.device):
+            self.h2d = torch.cuda.Stream(device=eng.device)
+            self.d2h = torch.cuda.Stream(device=eng.device)
+            self.flow_buf = eng.empty((batch, H, W, 2), torch.float32)
+            self.slots = []
+            for _ in range(n_slots):
+                self.slots.append(dict(
+                    prev=eng.empty((batch, H, W), torch.uint8), next=eng.empty((batch, H, W), torch.uint8),
+                    counts=torch.empty((2, batch), dtype=torch.int32).pin_memory(),
+                    labels=torch.empty((batch * self.cap,), dtype=torch.int32).pin_memory(),
+                    indices=torch.empty((batch * self.cap * 2,), dtype=torch.int32).pin_memory(),
+                    summary=torch.empty((batch * max_clusters * 8,), dtype=torch.float64).pin_memory(),
+                    ev_h2d=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_d2h=torch.cuda.Event(),
+                    res=None, busy=False))
+        self.h2d_bytes = 2 * batch * H * W
+        self.d2h_bytes = 0
+
+    def submit(self, slot: int, prev_host: torch.Tensor, next_host: torch.Tensor):
+        s = self.slots[slot]
+        if s["busy"]:
+            raise RuntimeError("slot still in flight: collect() it first")
+        eng = self.eng
+        with torch.cuda.device(eng.device):
+            with torch.cuda.stream(self.h2d):
+                s["prev"].copy_(prev_host, non_blocking=True)
+                s["next"].copy_(next_host, non_blocking=True)
+                s["ev_h2d"].record(self.h2d)
+            eng.stream.wait_event(s["ev_h2d"])
+            px, py, alpha, eps, ms = self.args
+            res = eng.flow_pipeline(s["prev"], s["next"], px, py, alpha, eps, ms, self.params, cap=self.cap,
+                                    max_clusters=self.max_clusters, keep_flow=False, flow_buf=self.flow_buf)
+            with torch.cuda.stream(eng.stream):
+                s["counts"][0].copy_(res.n_valid, non_blocking=True)
+                s["counts"][1].copy_(res.n_clusters, non_blocking=True)
+                s["ev_done"].record(eng.stream)
+        s["res"] = res
+        s["busy"] = True
+
+    def collect(self, slot: int):
+        """-> (n_valid[B], n_clusters[B], labels[B,nmax], indices[B,nmax,2], summary[B,kmax,8]) numpy views
+        into the slot's pinned buffers (valid until the slot is submitted again)."""
+        s = self.slots[slot]
+        if not s["busy"]:
+            raise RuntimeError("nothing submitted on this slot")
+        s["ev_done"].synchronize()
+        counts = s["counts"].numpy()
+        nmax = int(min(counts[0].max(), self.cap))
+        kmax = int(min(counts[1].max(), self.max_clusters))
+        res = s["res"]
+        B = self.B
+        with torch.cuda.device(self.eng.device):
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(s["ev_done"])
+                lab = s["labels"][:B * nmax].view(B, nmax)
+                idx = s["indices"][:B * nmax * 2].view(B, nmax, 2)
+                summ = s["summary"][:B * kmax * 8].view(B, kmax, 8)
+                if nmax:
+                    lab.copy_(res.labels[:, :nmax], non_blocking=True)
+                    idx.copy_(res.indices[:, :nmax], non_blocking=True)
+                if kmax:
+                    summ.copy_(res.summary[:, :kmax], non_blocking=True)
+                s["ev_d2h"].record(self.d2h)
+            s["ev_d2h"].synchronize()
+        self.d2h_bytes = counts.nbytes + lab.numel() * 4 + idx.numel() * 4 + summ.numel() * 8
+        s["res"] = None
+        s["busy"] = False
+        return counts[0], counts[1], lab.numpy(), idx.numpy(), summ.numpy()
