@@ -99,7 +99,8 @@ def test_stage_flow_iter_fused_equals_unfused(engine):
     fused = host(engine.fb_flow_iter(planar(R0), planar(R1), dev(flow[None]), 15))[0]
     M = engine.fb_update_matrices(planar(R0), planar(R1), dev(flow[None]))
     unfused = host(engine.fb_blur_solve(M, 15))[0]
-    assert np.array_equal(fused, unfused)
+    # different kernels (row-marching vs tiled) sum the same windows in a different order
+    assert np.abs(fused - unfused).max() <= 1e-5 * max(1.0, np.abs(unfused).max())
     want = fb.blur_solve(fb.update_matrices(R0, R1, flow), 15)
     assert np.abs(fused - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
 
@@ -162,7 +163,8 @@ def test_unfused_variant_matches_fused(engine):
     a, b = synth.bev_pair(8, 200, 200)
     f0 = host(engine.farneback(dev(a), dev(b), farneback_params(variant=0)))
     f1 = host(engine.farneback(dev(a), dev(b), farneback_params(variant=1)))
-    assert np.array_equal(f0, f1)
+    d = np.abs(f0 - f1)
+    assert d.mean() <= 1e-5 and d.max() <= 1e-2          # same algorithm, different summation order
 
 
 def test_zero_and_identical_frames(engine):
