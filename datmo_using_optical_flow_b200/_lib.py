@@ -74,6 +74,8 @@ SIGNATURES = {
     "datmo_bev_bins": (_i, [_d, _d, _d]),
     "datmo_bev_rasterize_dev": (_i, [_vp, _vp, _i, _i64, _d, _d, _d, _d, _i, _i, _d, _d, _d, _vp]),
     "datmo_bev_rasterize_host": (_i, [_vp, _vp, _i, _i64, _d, _d, _d, _d, _i, _i, _d, _d, _d, _vp]),
+    "datmo_roi_filter_dev": (_i, [_vp, _vp, _i, _i64, C.POINTER(_d), _vp, C.POINTER(_i64)]),
+    "datmo_expand_points_dev": (_i, [_vp, _vp, _i64, _i, _d, _vp, _u64, _vp]),
     "datmo_ransac_ground_dev": (_i, [_vp, _vp, _i, _i64, _i, _d, _i, _i, _u64] + [_vp] * 7),
     "datmo_preprocess_dev": (_i, [_vp, _vp, _i64, _i, _d, _i, _i, _u64, _vp, C.POINTER(_d), _i, _d, _vp, _d, _d, _d,
                                   _d, _i, _i, _d, _vp, C.POINTER(_i64)]),

@@ -35,10 +35,11 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     hsh = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "datmo_b200.h"), __file__]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    files += [os.path.join(INCLUDE, "datmo_b200.h"), __file__]
     for path in files:
         with open(path, "rb") as fh:
-            hsh.update(path.encode())
+            hsh.update(os.path.basename(path).encode())   # path-independent: the prebuilt .so travels
             hsh.update(fh.read())
     return hsh.hexdigest()
 
@@ -52,6 +53,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = _nvcc()
+    # several ranks may import at once: one builds, the others wait and re-check
+    import fcntl
+    lock = open(os.path.join(LIB_DIR, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
+            with open(STAMP) as fh:
+                if fh.read().strip() == digest:
+                    return LIB_PATH
+        return _build_locked(nvcc, digest, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc: str, digest: str, verbose: bool) -> str:
     objs = []
     procs = []
     for src in SOURCES:

@@ -220,6 +220,55 @@ __global__ void __launch_bounds__(256) k_bev_norm(const double* __restrict__ val
     bev[i] = o;
 }
 
+// ---- filter_points_in_roi (main.py:30-36) as a stable device compaction ----------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) k_roi_flags(const void* __restrict__ pts, int64_t n, double x0, double x1,
+                                                   double y0, double y1, double z0, double z1,
+                                                   uint8_t* __restrict__ flags) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x, y, z;
+    load_point<LAYOUT>(pts, i, x, y, z);
+    flags[i] = x >= x0 && x <= x1 && y >= y0 && y <= y1 && z >= z0 && z <= z1;   // closed intervals
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) k_roi_scatter(const void* __restrict__ pts, int64_t n,
+                                                     const uint8_t* __restrict__ flags,
+                                                     const int32_t* __restrict__ rank, void* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    const int64_t o = rank[i];
+    if (LAYOUT == DATMO_PTS_F64_XYZ) {
+        const double* p = static_cast<const double*>(pts) + 3 * i;
+        double* q = static_cast<double*>(out) + 3 * o;
+        q[0] = p[0], q[1] = p[1], q[2] = p[2];
+    } else {
+        static_cast<float4*>(out)[o] = static_cast<const float4*>(pts)[i];
+    }
+}
+
+// ---- increase_point_density (main.py:38-57): consecutive copies + noise ---------------------------
+__global__ void __launch_bounds__(256) k_expand(const double* __restrict__ pts, int64_t n, int expansion,
+                                                double noise_std, const double* __restrict__ noise, uint64_t seed,
+                                                double* __restrict__ out) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n * expansion) return;
+    const int64_t i = t / expansion;
+    double nx_, ny_, nz_;
+    if (noise) {
+        nx_ = noise[3 * t], ny_ = noise[3 * t + 1], nz_ = noise[3 * t + 2];
+    } else {
+        double a, b, c, d;
+        normal2(seed, 2 * static_cast<uint64_t>(t), a, b);
+        normal2(seed, 2 * static_cast<uint64_t>(t) + 1, c, d);
+        nx_ = a * noise_std, ny_ = b * noise_std, nz_ = c * noise_std;
+    }
+    out[3 * t] = __dadd_rn(pts[3 * i], nx_);
+    out[3 * t + 1] = __dadd_rn(pts[3 * i + 1], ny_);
+    out[3 * t + 2] = __dadd_rn(pts[3 * i + 2], nz_);
+}
+
 struct BevWs {
     uint32_t* cnt;
     double* sum;
@@ -410,6 +459,66 @@ int datmo_preprocess_dev(datmo_handle_t h, const float* pts, int64_t n, int flip
     DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
     if (n_roi) *n_roi = static_cast<int64_t>(roi_count);
     return roi_count == 0 ? DATMO_E_EMPTY : DATMO_OK;
+}
+
+int datmo_roi_filter_dev(datmo_handle_t h, const void* pts, int layout, int64_t n, const double roi[6], void* out,
+                         int64_t* n_out) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, (pts || n == 0) && roi && (out || n == 0) && n_out && n >= 0, "null pointer");
+    DATMO_REQUIRE(h, layout == DATMO_PTS_F64_XYZ || layout == DATMO_PTS_F32_XYZW, "unknown point layout");
+    DATMO_REQUIRE(h, n < (int64_t(1) << 31), "too many points");
+    *n_out = 0;
+    if (n == 0) return DATMO_OK;
+    const int nblk = static_cast<int>(ceil_div64(n, 4096));
+    uint8_t* flags;
+    int32_t *rank, *bsum, *total;
+    for (int pass = 0; pass < 2; ++pass) {
+        Bump bump(pass ? h->ws : nullptr);
+        flags = bump.take<uint8_t>(n);
+        rank = bump.take<int32_t>(n);
+        bsum = bump.take<int32_t>(nblk);
+        total = bump.take<int32_t>(1);
+        if (!pass) DATMO_TRY(datmo_ws_reserve(h, bump.off));
+    }
+    const unsigned g = static_cast<unsigned>(ceil_div64(n, 256));
+    {
+        LaunchScope ls(h, DATMO_TAG_BEV);
+        if (layout == DATMO_PTS_F64_XYZ)
+            k_roi_flags<DATMO_PTS_F64_XYZ><<<g, 256, 0, h->stream>>>(pts, n, roi[0], roi[1], roi[2], roi[3], roi[4],
+                                                                    roi[5], flags);
+        else
+            k_roi_flags<DATMO_PTS_F32_XYZW><<<g, 256, 0, h->stream>>>(pts, n, roi[0], roi[1], roi[2], roi[3], roi[4],
+                                                                     roi[5], flags);
+    }
+    DATMO_POST_LAUNCH(h);
+    DATMO_TRY(datmo_flag_scan(h, flags, n, 1, bsum, total, rank, DATMO_TAG_BEV, 1));
+    {
+        LaunchScope ls(h, DATMO_TAG_BEV);
+        if (layout == DATMO_PTS_F64_XYZ)
+            k_roi_scatter<DATMO_PTS_F64_XYZ><<<g, 256, 0, h->stream>>>(pts, n, flags, rank, out);
+        else
+            k_roi_scatter<DATMO_PTS_F32_XYZW><<<g, 256, 0, h->stream>>>(pts, n, flags, rank, out);
+    }
+    DATMO_POST_LAUNCH(h);
+    int32_t cnt = 0;
+    DATMO_CHECK_CUDA(h, cudaMemcpyAsync(&cnt, total, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+    DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    *n_out = cnt;
+    return DATMO_OK;
+}
+
+int datmo_expand_points_dev(datmo_handle_t h, const double* pts, int64_t n, int expansion, double noise_std,
+                            const double* noise, uint64_t seed, double* out) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, (pts || n == 0) && out && n >= 0 && expansion >= 1, "bad arguments");
+    if (n == 0) return DATMO_OK;
+    {
+        LaunchScope ls(h, DATMO_TAG_BEV);
+        k_expand<<<static_cast<unsigned>(ceil_div64(n * expansion, 256)), 256, 0, h->stream>>>(pts, n, expansion,
+                                                                                              noise_std, noise, seed, out);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
 }
 
 }  // extern "C"

@@ -95,4 +95,8 @@ struct LaunchScope {
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// dbscan.cu: exclusive rank of every flagged item of [batch][n]; block_sums needs batch * ceil(n / 4096) ints
+int datmo_flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, int32_t* block_sums, int32_t* totals,
+                    int32_t* rank, int tag, int sparse);
+
 #define DATMO_POST_LAUNCH(h) DATMO_CHECK_CUDA(h, cudaGetLastError())

@@ -402,8 +402,11 @@ static int dbg_tag(int sub) {
     return on ? sub : DATMO_TAG_DBSCAN;
 }
 
-int flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, int32_t* block_sums, int32_t* totals,
-              int32_t* rank, int tag, int sparse) {
+}  // namespace
+
+// shared with bev.cu (ROI compaction): exclusive rank of every flagged item of [batch][n]
+int datmo_flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, int32_t* block_sums, int32_t* totals,
+                    int32_t* rank, int tag, int sparse) {
     int nblk = static_cast<int>(ceil_div64(n, SCAN_ITEMS));
     dim3 g(nblk, batch);
     {
@@ -423,6 +426,8 @@ int flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, int32_t*
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
 }
+
+namespace {
 
 // ---- cluster summaries ------------------------------------------------------------------------
 // Integer moments (n, sum r, sum c, sum rr, sum rc, sum cc) are accumulated exactly in uint64;
@@ -539,7 +544,7 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
         total = bump.off;
         if (!pass) DATMO_TRY(datmo_ws_reserve(h, total));
     }
-    DATMO_TRY(flag_scan(h, valid, n, batch, bsum, n_valid, rank, dbg_tag(0), 1));
+    DATMO_TRY(datmo_flag_scan(h, valid, n, batch, bsum, n_valid, rank, dbg_tag(0), 1));
     dim3 g(ceil_div(W, 256), H, batch);
     {
         LaunchScope ls(h, dbg_tag(1));
@@ -582,7 +587,7 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
     }
     DATMO_POST_LAUNCH(h);
     int32_t* ncl_out = n_clusters ? n_clusters : ncl;
-    DATMO_TRY(flag_scan(h, is_root, n, batch, bsum, ncl_out, root_rank, dbg_tag(0), 1));
+    DATMO_TRY(datmo_flag_scan(h, is_root, n, batch, bsum, ncl_out, root_rank, dbg_tag(0), 1));
     {
         LaunchScope ls(h, dbg_tag(6));
         k_labels<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, parent, rank, root_rank, H, W, r, eps2, cap, labels,

@@ -304,6 +304,33 @@ class Engine:
                                                          float(b), float(h_max), _ptr(bev)))
         return bev
 
+    def roi_filter(self, points: torch.Tensor, roi_bounds):
+        """filter_points_in_roi on the device (stable compaction) -> points inside the closed ROI box."""
+        with self.on_stream():
+            points = points.contiguous()
+            layout = self._points_layout(points)
+            out = torch.empty_like(points)
+            roi = (C.c_double * 6)(*[float(v) for v in roi_bounds])
+            n_out = C.c_int64(0)
+            self._check(self.lib.datmo_roi_filter_dev(self.h, _ptr(points), layout, points.shape[0], roi, _ptr(out),
+                                                      C.byref(n_out)))
+        return out[:n_out.value]
+
+    def expand_points(self, points: torch.Tensor, expansion: int, noise_std: float = 0.01,
+                      noise: torch.Tensor | None = None, seed: int = 0):
+        """increase_point_density on the device: f64 [n,3] -> f64 [n*expansion,3]."""
+        with self.on_stream():
+            points = points.to(torch.float64).contiguous()
+            n = points.shape[0]
+            out = self.empty((n * expansion, 3), torch.float64)
+            if noise is not None:
+                noise = noise.to(torch.float64).contiguous()
+                if noise.numel() != n * expansion * 3:
+                    raise ValueError("noise must have the shape of the expanded cloud")
+            self._check(self.lib.datmo_expand_points_dev(self.h, _ptr(points), n, int(expansion), float(noise_std),
+                                                         _ptr(noise), C.c_uint64(seed), _ptr(out)))
+        return out
+
     def ransac_ground(self, points: torch.Tensor, distance_threshold=0.5, ransac_n=5, num_iterations=5000, seed=0,
                       flip_x=False, return_hypotheses=False):
         """segment_plane on the device -> dict(plane, refit, inlier_mask, best[, hyp_*])."""

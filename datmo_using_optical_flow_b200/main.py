@@ -41,30 +41,34 @@ def _is_np(*xs) -> bool:
 # ---------------------------------------------------------------------------------------------
 # preprocessing (main.py:30-126)
 # ---------------------------------------------------------------------------------------------
-def filter_points_in_roi(points, roi_bounds):
-    """main.py:30-36 — closed-interval box crop.  Host-side view selection: it is a
-    memory-bound boolean take that the fused device path (``preprocess_points``)
-    folds into the rasteriser; kept here for callers that use it on its own."""
-    x_min, x_max, y_min, y_max, z_min, z_max = roi_bounds
-    p = points
-    keep = ((p[:, 0] >= x_min) & (p[:, 0] <= x_max) & (p[:, 1] >= y_min) & (p[:, 1] <= y_max)
-            & (p[:, 2] >= z_min) & (p[:, 2] <= z_max))
-    return p[keep]
+def filter_points_in_roi(points, roi_bounds, engine=None):
+    """main.py:30-36 — closed-interval box crop, order preserved (device compaction)."""
+    eng = engine or default_engine()
+    as_np = _is_np(points)
+    pts = _to_dev(eng, points)
+    if pts.dim() != 2 or pts.shape[1] < 3:
+        raise ValueError("points must be (N, 3)")
+    if not (pts.dtype == torch.float32 and pts.shape[1] == 4):
+        pts = pts[:, :3].to(torch.float64)
+    out = eng.roi_filter(pts, roi_bounds)
+    return out.cpu().numpy() if as_np else out
 
 
-def increase_point_density(points, expansion_factor=2, noise_std=0.01, noise=None):
+def increase_point_density(points, expansion_factor=2, noise_std=0.01, noise=None, seed=None, engine=None):
     """main.py:38-57 — ``expansion_factor`` consecutive copies of every point plus
-    N(0, noise_std).  ``noise`` (same shape as the result) may be passed to make
-    the call reproducible; the reference draws from numpy's unseeded global RNG."""
-    if isinstance(points, torch.Tensor):
-        rep = points.repeat_interleave(int(expansion_factor), dim=0)
-        if noise is None:
-            noise = torch.randn(rep.shape, dtype=rep.dtype, device=rep.device) * noise_std
-        return rep + noise
-    rep = np.repeat(points, expansion_factor, axis=0)
-    if noise is None:
-        noise = np.random.normal(scale=noise_std, size=rep.shape)
-    return rep + noise
+    N(0, noise_std).  ``noise`` (same shape as the result) makes the call reproducible;
+    otherwise noise is drawn on the device (the reference uses numpy's unseeded global RNG)."""
+    eng = engine or default_engine()
+    as_np = _is_np(points)
+    pts = _to_dev(eng, points)[:, :3].to(torch.float64)
+    nz = None if noise is None else _to_dev(eng, noise, torch.float64)
+    if seed is None:
+        seed = int(np.random.randint(0, 2**31 - 1))
+    out = eng.expand_points(pts, int(expansion_factor), noise_std, nz, seed)
+    if as_np:
+        eng.synchronize()
+        return out.cpu().numpy()
+    return out
 
 
 def compute_bev_grid(points, grid_resolution, x_range, y_range, a=0.5, b=0.5, h_max=5.0, engine=None):

@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing: one process per GPU, work sharded by frame pair or by sequence,
+no collective on the data path; torch.distributed only gathers tracks and metrics.
+
+Frame pairs are independent through BEV -> flow -> clusters; the EKF carries state
+across the pairs of ONE sequence (/root/reference/Optical_flow/main.py:553-634), so
+throughput workloads shard by pair and end-to-end workloads shard by sequence
+(SURVEY.md §8 e).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block of `total` items owned by `rank`: (start, count).  Blocks differ by at
+    most one item and concatenate, in rank order, to range(total)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank / world")
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+def shard_sequences(n_sequences: int, rank: int, world: int) -> list[int]:
+    start, count = shard_range(n_sequences, rank, world)
+    return list(range(start, start + count))
+
+
+def _is_dist() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def gather_tracks(local: np.ndarray | torch.Tensor, max_tracks: int, device=None) -> list[np.ndarray]:
+    """All-gather of per-shard track tables.  local: (n, 6) rows [id, s0, s1, s2, s3, confirmed].
+    Every rank contributes a fixed (max_tracks, 6) float64 block (NaN padded) plus its count;
+    returns the unpadded table of every rank, in rank order, on every rank."""
+    t = torch.as_tensor(np.asarray(local, dtype=np.float64).reshape(-1, 6))
+    n = min(len(t), max_tracks)
+    buf = torch.full((max_tracks * 6 + 1,), float("nan"), dtype=torch.float64)
+    buf[0] = n
+    buf[1:1 + n * 6] = t[:n].reshape(-1)
+    if not _is_dist():
+        return [t[:n].numpy()]
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if dist.get_backend() == "nccl" else torch.device("cpu"))
+    buf = buf.to(dev)
+    out = [torch.empty_like(buf) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, buf)
+    res = []
+    for o in out:
+        o = o.cpu()
+        k = int(o[0].item())
+        res.append(o[1:1 + k * 6].reshape(k, 6).numpy())
+    return res
+
+
+def reduce_metrics(values: dict[str, float], op: str = "sum", device=None) -> dict[str, float]:
+    """All-reduce a small dict of scalars (timing, parity counters)."""
+    keys = sorted(values)
+    t = torch.tensor([float(values[k]) for k in keys], dtype=torch.float64)
+    if _is_dist():
+        dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                 if dist.get_backend() == "nccl" else torch.device("cpu"))
+        t = t.to(dev)
+        dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN}[op])
+        t = t.cpu()
+    return {k: float(v) for k, v in zip(keys, t.tolist())}

@@ -1,0 +1,119 @@
+"""Host-side tracking stage: EKF per track, nearest-track gating, M-of-N track management.
+
+Restates the behaviour of the reference's ``EKF`` / ``track_clusters`` /
+``manage_tracks`` and the lifetime bookkeeping of its driver loop
+(/root/reference/Optical_flow/main.py:437-515, 618-634).  It is O(#clusters)
+4x4 scalar work per frame pair and stays on the host; the GPU
+hands it the per-cluster summaries.  The reference's quirks are reproduced, not
+fixed, because the tracks are part of its observable output:
+  * the "state" is [row, col, mean vx, mean vy] but predict() treats state[2] as a
+    heading and state[3] as a speed, with the cluster's (vx, vy) as (v, omega);
+  * association compares [centroid, eigenvalues] with [x, y, 0, 0] under gamma;
+  * tracks not matched in a frame are dropped; every unmatched cluster of one frame
+    gets the same new id (max existing id + 1), so only the last one survives;
+  * two clusters may update the same track in one frame.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class Track:
+    state: np.ndarray                      # (4,)
+    P: np.ndarray = field(default_factory=lambda: np.eye(4))
+    F: np.ndarray = field(default_factory=lambda: np.eye(4))
+
+
+class TrackManager:
+    """tracks / lifetimes / confirmed set of one sequence."""
+
+    def __init__(self, process_noise=None, measurement_noise=None, gamma=0.5, M1=1, N1=4, M2=10, N2=15):
+        # main.py:618 and :634 hard-code these
+        self.Q = np.eye(4) * 0.1 if process_noise is None else np.asarray(process_noise, dtype=float)
+        self.R = np.eye(4) * 0.05 if measurement_noise is None else np.asarray(measurement_noise, dtype=float)
+        self.gamma = gamma
+        self.M1, self.N1, self.M2, self.N2 = M1, N1, M2, N2
+        self.tracks: dict[int, Track] = {}
+        self.lifetimes: dict[int, int] = {}
+        self.confirmed: set[int] = set()
+
+    # -- EKF ---------------------------------------------------------------------------------
+    def _predict(self, t: Track, dt: float, v: float, omega: float):
+        theta = t.state[2]
+        t.F[0, 2] = dt
+        t.F[1, 3] = dt
+        speed = t.state[3]
+        t.state[0] += speed * math.cos(theta) * dt
+        t.state[1] += speed * math.sin(theta) * dt
+        t.state[2] += omega * dt
+        t.state[3] += v * dt
+        t.P = t.F @ t.P @ t.F.T + self.Q
+
+    def _update(self, t: Track, z: np.ndarray):
+        # H = I
+        innov = z - t.state
+        S = t.P + self.R
+        K = t.P @ np.linalg.inv(S)
+        t.state = t.state + K @ innov
+        t.P = (np.eye(4) - K) @ t.P
+
+    # -- association -----------------------------------------------------------------------------
+    def associate_and_update(self, clusters: dict, dt: float):
+        """clusters: {label: {'centroid', 'measurement', 'eigenvalues'}} in label order."""
+        old = self.tracks
+        new: dict[int, Track] = {}
+        next_id = max(old.keys(), default=0) + 1
+        for _, cl in clusters.items():
+            feat = np.array([*cl["centroid"], *np.real(cl["eigenvalues"])], dtype=float)
+            best, best_d = None, math.inf
+            for tid, t in old.items():
+                d = float(np.linalg.norm(feat - np.array([t.state[0], t.state[1], 0.0, 0.0])))
+                if d < best_d and d < self.gamma:
+                    best, best_d = tid, d
+            z = np.asarray(cl["measurement"], dtype=float)
+            if best is not None:
+                t = old[best]
+                self._predict(t, dt, z[2], z[3])
+                self._update(t, z)
+                new[best] = t
+            else:
+                new[next_id] = Track(state=z.copy())
+        self.tracks = new
+        return new
+
+    # -- lifetimes + M-of-N --------------------------------------------------------------------------
+    def step_lifetimes(self):
+        for tid in list(self.lifetimes):
+            if tid in self.tracks:
+                self.lifetimes[tid] += 1
+            else:
+                del self.lifetimes[tid]
+        for tid in self.tracks:
+            self.lifetimes.setdefault(tid, 1)
+        for tid in list(self.tracks):
+            life = self.lifetimes[tid]
+            if tid in self.confirmed:
+                if life > self.N2 and life - self.M2 <= self.N2:
+                    del self.tracks[tid]
+            elif life >= self.N1 and life - self.M1 <= self.N1:
+                self.confirmed.add(tid)
+
+    def update(self, clusters: dict, dt: float):
+        """One frame pair: what main.py:618-634 does between extract_cluster_data and the next pair."""
+        self.associate_and_update(clusters, dt)
+        self.step_lifetimes()
+        return self.tracks
+
+    def as_array(self, max_tracks: int | None = None) -> np.ndarray:
+        """(n, 6) float64 rows [track id, row, col, s2, s3, confirmed] sorted by id (padded with NaN)."""
+        rows = [[tid, *t.state.tolist(), float(tid in self.confirmed)] for tid, t in sorted(self.tracks.items())]
+        arr = np.array(rows, dtype=np.float64).reshape(-1, 6)
+        if max_tracks is not None:
+            out = np.full((max_tracks, 6), np.nan)
+            out[:min(len(arr), max_tracks)] = arr[:max_tracks]
+            return out
+        return arr

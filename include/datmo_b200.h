@@ -106,7 +106,8 @@ int datmo_farneback_host(datmo_handle_t h, const void* prev, const void* next, i
                          int batch, const datmo_farneback_params* p, float* flow);
 
 /* stage-level entry points (device pointers), used by the parity tests to diff
- * each step against the oracle.  R arrays are planar float [batch][5][h][w]. */
+ * each step against the oracle.  R and M arrays cross the ABI as planar float [batch][5][h][w]
+ * (internally R is kept as float4 + float per pixel). */
 int datmo_fb_pyramid_image_dev(datmo_handle_t h, const void* img, int dtype, int H, int W, int batch,
                                int ksize, double sigma, int h_out, int w_out, float* out);
 int datmo_fb_polyexp_dev(datmo_handle_t h, const float* img, int hh, int ww, int batch, int poly_n,
@@ -171,6 +172,18 @@ int datmo_bev_rasterize_dev(datmo_handle_t h, const void* pts, int layout, int64
 int datmo_bev_rasterize_host(datmo_handle_t h, const void* pts, int layout, int64_t n, double res_x,
                              double res_y, double x_lo, double y_lo, int nx, int ny, double a, double b,
                              double h_max, uint8_t* bev);
+
+/* ---- ROI crop and density expansion ---------------------------------------------------------
+ * datmo_roi_filter_dev replaces filter_points_in_roi, main.py:30-36: keeps, in order, the points
+ * with x, y, z inside the CLOSED intervals roi = {x_min, x_max, y_min, y_max, z_min, z_max}.
+ * out: room for n points in the same layout; *n_out (host) receives the count.  Synchronises.
+ * datmo_expand_points_dev replaces increase_point_density, main.py:38-57: `expansion`
+ * consecutive copies of every point plus noise (double [n*expansion][3], or NULL to draw
+ * N(0, noise_std) from seed).  pts / out: double [n][3] / [n*expansion][3]. */
+int datmo_roi_filter_dev(datmo_handle_t h, const void* pts, int layout, int64_t n, const double roi[6], void* out,
+                         int64_t* n_out);
+int datmo_expand_points_dev(datmo_handle_t h, const double* pts, int64_t n, int expansion, double noise_std,
+                            const double* noise, uint64_t seed, double* out);
 
 /* ---- RANSAC ground plane -------------------------------------------------------------
  * Replaces flipped_pcd.segment_plane(0.5, 5, 5000), main.py:73 (Open3D).  Scores

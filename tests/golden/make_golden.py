@@ -126,5 +126,51 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 
+
+
+def tracker_golden():
+    """Reference EKF / track_clusters / manage_tracks + the driver's lifetime bookkeeping
+    (main.py:437-515, 618-634) on a seeded stream of cluster dictionaries."""
+    ref = ref_loader.load_reference_main()
+    rng = np.random.default_rng(77)
+    frames = []
+    centers = rng.uniform(20, 180, (4, 2))
+    vels = rng.uniform(-0.3, 0.3, (4, 2))
+    for f in range(24):
+        cl = {}
+        k = 0
+        for j in range(4):
+            if rng.uniform() < 0.15:
+                continue                                   # missed detection
+            c = centers[j] + vels[j] * f * (0.2 if j < 2 else 3.0) + rng.normal(0, 0.05, 2)
+            eig = np.abs(rng.normal(0.05, 0.02, 2)) if j < 3 else np.abs(rng.normal(4.0, 1.0, 2))
+            cl[k] = dict(centroid=c, measurement=[c[0], c[1], vels[j][0], vels[j][1]], eigenvalues=eig)
+            k += 1
+        frames.append(cl)
+    tracks, lifetimes, confirmed = {}, {}, set()
+    out = {"versions": versions(), "n_frames": np.array(len(frames))}
+    for f, cl in enumerate(frames):
+        keys = sorted(cl)
+        out[f"f{f}_centroid"] = np.array([cl[k]["centroid"] for k in keys]).reshape(-1, 2)
+        out[f"f{f}_meas"] = np.array([cl[k]["measurement"] for k in keys]).reshape(-1, 4)
+        out[f"f{f}_eig"] = np.array([cl[k]["eigenvalues"] for k in keys]).reshape(-1, 2)
+        tracks = ref.track_clusters(tracks, cl, 1.0, np.eye(4) * 0.1, np.eye(4) * 0.05, gamma=0.5)
+        for tid in list(lifetimes.keys()):
+            if tid in tracks:
+                lifetimes[tid] += 1
+            else:
+                del lifetimes[tid]
+        for tid in tracks:
+            if tid not in lifetimes:
+                lifetimes[tid] = 1
+        ref.manage_tracks(tracks, lifetimes, confirmed, M1=1, N1=4, M2=10, N2=15)
+        rows = [[tid, *tracks[tid].state.tolist(), float(tid in confirmed)] for tid in sorted(tracks)]
+        out[f"f{f}_tracks"] = np.array(rows, dtype=np.float64).reshape(-1, 6)
+    np.savez_compressed(os.path.join(OUT, "tracks.npz"), **out)
+    print("tracks.npz", os.path.getsize(os.path.join(OUT, "tracks.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--tracks-only" not in sys.argv:
+        main()
+    tracker_golden()

@@ -248,3 +248,40 @@ def test_preprocess_with_device_ransac_and_device_noise(engine):
     # empty ROI -> None, like the reference (main.py:84-86)
     assert main.preprocess_points(pts, c["grid_resolution"], c["x_range"], c["y_range"], 2.0,
                                   [1000, 1001, 1000, 1001, 0, 1], engine=engine) is None
+
+
+# ---- ROI crop / density expansion as device ops ---------------------------------------------------
+def test_roi_filter_and_expansion_device(engine, golden):
+    g = golden("bev.npz")
+    got = main.filter_points_in_roi(g["roi_points"], [float(v) for v in g["roi_bounds"]], engine=engine)
+    assert np.array_equal(got, g["roi_out"])
+    rng = np.random.default_rng(8)
+    p = rng.uniform(-12, 12, (50_000, 3))
+    roi = [-10, 10, -10, 10, -3, 1]
+    assert np.array_equal(main.filter_points_in_roi(p, roi, engine=engine), bev_np.filter_points_in_roi(p, roi))
+    p4 = np.concatenate([p, rng.uniform(size=(len(p), 1))], axis=1).astype(np.float32)
+    keep = ((p4[:, 0] >= -10) & (p4[:, 0] <= 10) & (p4[:, 1] >= -10) & (p4[:, 1] <= 10) & (p4[:, 2] >= -3) & (p4[:, 2] <= 1))
+    assert np.array_equal(host(engine.roi_filter(dev(p4), roi)), p4[keep])
+    assert main.filter_points_in_roi(np.zeros((0, 3)), roi, engine=engine).shape == (0, 3)
+    noise = rng.normal(scale=0.01, size=(len(p) * 10, 3))
+    exp = main.increase_point_density(p, 10, 0.01, noise=noise, engine=engine)
+    assert np.array_equal(exp, bev_np.increase_point_density(p, 10, noise=noise))
+    drawn = main.increase_point_density(p[:2000], 10, 0.01, seed=5, engine=engine)
+    d = drawn - np.repeat(p[:2000], 10, axis=0)
+    assert abs(d.std() - 0.01) < 5e-4 and abs(d.mean()) < 3e-4          # N(0, 0.01) on every coordinate
+
+
+# ---- the sequence driver (preprocess -> flow -> clusters -> tracker) ---------------------------------
+def test_sequence_pipeline_tracks_the_mover(engine):
+    from datmo_using_optical_flow_b200.pipeline import process_clouds
+    cfg = dict(grid_resolution=[0.25, 0.25], x_range=[-50.0, 50.0], y_range=[-50.0, 50.0], z_max=2.0,
+               roi_bounds=[-50, 50, -50, 50, -3, 1], dt=1.0)
+    clouds = [synth.lidar_sweep(3, f, 32, 60_000, 1, dt=0.1) for f in range(4)]
+    out = process_clouds(clouds, cfg, engine=engine, seed=1)
+    assert len(out["bevs"]) == 4 and all(b is not None and b.shape == (400, 400) for b in out["bevs"])
+    assert len(out["pairs"]) == 3
+    done = [p for p in out["pairs"] if not p["skipped"]]
+    assert done, "every pair was skipped"
+    for p in done:
+        assert len(p["labels"]) == len(p["indices"]) and p["tracks"].shape[1] == 6
+        assert set(p["clusters"]) == set(range(len(p["clusters"])))

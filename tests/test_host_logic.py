@@ -1,0 +1,154 @@
+"""CPU: host-side logic — tracker vs the reference's EKF golden, sharding + gloo gathers
+(world_size 2), PCD reader, synthetic generators."""
+import os
+import socket
+import struct
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from datmo_using_optical_flow_b200 import sharding, synth
+from datmo_using_optical_flow_b200.tracker import TrackManager
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- tracker ------------------------------------------------------------------------------------
+def test_tracker_matches_reference_golden(golden):
+    g = golden("tracks.npz")
+    tm = TrackManager()
+    for f in range(int(g["n_frames"])):
+        cen, meas, eig = g[f"f{f}_centroid"], g[f"f{f}_meas"], g[f"f{f}_eig"]
+        clusters = {k: dict(centroid=cen[k], measurement=meas[k].tolist(), eigenvalues=eig[k]) for k in range(len(cen))}
+        tm.update(clusters, 1.0)
+        want = g[f"f{f}_tracks"]
+        got = tm.as_array()
+        assert got.shape == want.shape, f
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, err_msg=f"frame {f}")
+    assert len(tm.confirmed) >= 1
+
+
+def test_tracker_reference_quirks():
+    tm = TrackManager()
+    far = {0: dict(centroid=np.array([10.0, 10.0]), measurement=[10.0, 10.0, 0.1, 0.0], eigenvalues=np.array([3.0, 3.0])),
+           1: dict(centroid=np.array([50.0, 50.0]), measurement=[50.0, 50.0, 0.0, 0.1], eigenvalues=np.array([3.0, 3.0]))}
+    tm.update(far, 1.0)
+    # both unmatched clusters get id 1 (max of the OLD table + 1): only the last survives
+    assert list(tm.tracks) == [1] and tm.tracks[1].state[0] == 50.0
+    tm.update({}, 1.0)
+    assert tm.tracks == {} and tm.lifetimes == {}          # unmatched tracks are dropped
+    nan = {0: dict(centroid=np.array([1.0, 1.0]), measurement=[1.0, 1.0, 0, 0], eigenvalues=np.array([np.nan, np.nan]))}
+    tm.update(nan, 1.0)
+    tm.update(nan, 1.0)                                       # NaN distance never matches -> always a new track
+    assert list(tm.tracks) == [2]
+    assert tm.as_array(max_tracks=3).shape == (3, 6) and np.isnan(tm.as_array(max_tracks=3)[1:]).all()
+
+
+# ---- sharding -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("total,world", [(4096, 8), (4096, 3), (8, 8), (5, 8), (0, 2), (100, 1)])
+def test_shard_range_partitions(total, world):
+    got = []
+    sizes = []
+    for r in range(world):
+        s, c = sharding.shard_range(total, r, world)
+        got += list(range(s, s + c))
+        sizes.append(c)
+    assert got == list(range(total))
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_range(10, 2, 2)
+
+
+def test_shard_sequences_cfg5():
+    assert [sharding.shard_sequences(8, r, 4) for r in range(4)] == [[0, 1], [2, 3], [4, 5], [6, 7]]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # each rank "processes" its shard of 11 pairs and of 3 sequences
+        s, c = sharding.shard_range(11, rank, world)
+        local_sum = float(sum(range(s, s + c)))
+        red = sharding.reduce_metrics({"pairs": c, "checksum": local_sum, "t": 1.0 + rank}, "sum")
+        mx = sharding.reduce_metrics({"t": 1.0 + rank}, "max")
+        tracks = np.array([[10 * rank + i, rank, i, 0.5, -0.5, i % 2] for i in range(rank + 2)], dtype=np.float64)
+        gathered = sharding.gather_tracks(tracks, max_tracks=4)
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), pairs=red["pairs"], checksum=red["checksum"], tmax=mx["t"],
+                 n=len(gathered), **{f"g{i}": g for i, g in enumerate(gathered)})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_and_reduce(tmp_path):
+    world = 2
+    mp.spawn(_gloo_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        d = np.load(tmp_path / f"r{r}.npz")
+        assert d["pairs"] == 11 and d["checksum"] == sum(range(11)) and d["tmax"] == 2.0
+        assert d["n"] == 2
+        assert d["g0"].shape == (2, 6) and d["g1"].shape == (3, 6)      # unpadded, in rank order, on every rank
+        assert d["g1"][2, 0] == 12.0
+
+
+def test_gather_tracks_single_process_and_truncation():
+    t = np.arange(30, dtype=np.float64).reshape(5, 6)
+    out = sharding.gather_tracks(t, max_tracks=3)
+    assert len(out) == 1 and np.array_equal(out[0], t[:3])
+    assert sharding.gather_tracks(np.zeros((0, 6)), 4)[0].shape == (0, 6)
+
+
+# ---- PCD reader ------------------------------------------------------------------------------------
+def _write_pcd(path, pts, binary):
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\n"
+           f"WIDTH {len(pts)}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {len(pts)}\nDATA {'binary' if binary else 'ascii'}\n")
+    with open(path, "wb") as fh:
+        fh.write(hdr.encode())
+        if binary:
+            fh.write(pts.astype("<f4").tobytes())
+        else:
+            for p in pts:
+                fh.write(("%.9g %.9g %.9g\n" % tuple(p)).encode())
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_read_pcd_roundtrip(tmp_path, binary):
+    from datmo_using_optical_flow_b200.main import read_pcd
+    pts = np.random.default_rng(0).uniform(-50, 50, (257, 3)).astype(np.float32)
+    path = str(tmp_path / "frame.pcd")
+    _write_pcd(path, pts, binary)
+    got = read_pcd(path)
+    assert got.dtype == np.float32 and got.shape == (257, 4)
+    assert np.array_equal(got[:, :3], pts) and not got[:, 3].any()
+    with open(path, "wb") as fh:
+        fh.write(b"FIELDS a b\nDATA ascii\n1 2\n")
+    with pytest.raises(ValueError):
+        read_pcd(path)
+
+
+# ---- synthetic inputs --------------------------------------------------------------------------------
+def test_synth_is_deterministic_and_sized():
+    a1, b1 = synth.bev_pair(7, 256, 320)
+    a2, b2 = synth.bev_pair(7, 256, 320)
+    assert np.array_equal(a1, a2) and np.array_equal(b1, b2) and a1.dtype == np.uint8 and a1.shape == (256, 320)
+    assert (a1 != b1).any()
+    p = synth.lidar_sweep(0, 0, 32, 60_000, 1)
+    assert p.dtype == np.float32 and p.shape[1] == 4 and 40_000 < len(p) < 80_000
+    assert np.array_equal(p, synth.lidar_sweep(0, 0, 32, 60_000, 1))
+    ground = np.abs(p[:, 2] + 2.5) < 0.1
+    assert 0.3 < ground.mean() < 0.98
+    q = synth.lidar_sweep(0, 5, 32, 60_000, 1)
+    assert len(q) != len(p) or not np.array_equal(p, q)          # the mover moved
