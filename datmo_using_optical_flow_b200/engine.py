@@ -458,26 +458,33 @@ class HostFlowPipeline:
         s["busy"] = True
 
     def collect(self, slot: int):
-        """-> (n_valid[B], n_clusters[B], labels[B,nmax], indices[B,nmax,2], summary[B,kmax,8]) numpy views
-        into the slot's pinned buffers (valid until the slot is submitted again)."""
+        """-> (n_valid[B], n_clusters[B], offsets[B+1], labels[sum n], indices[sum n, 2], summary[B,kmax,8])
+        numpy views into the slot's pinned buffers (valid until the slot is submitted again).  The labels /
+        indices of pair b are rows offsets[b]:offsets[b+1]; only the valid prefix of every pair crosses
+        the bus (one contiguous device-to-host copy per pair and array)."""
         s = self.slots[slot]
         if not s["busy"]:
             raise RuntimeError("nothing submitted on this slot")
         s["ev_done"].synchronize()
         counts = s["counts"].numpy()
-        nmax = int(min(counts[0].max(), self.cap))
+        nv = np.minimum(counts[0], self.cap).astype(np.int64)
+        offsets = np.zeros(self.B + 1, dtype=np.int64)
+        np.cumsum(nv, out=offsets[1:])
+        total = int(offsets[-1])
         kmax = int(min(counts[1].max(), self.max_clusters))
         res = s["res"]
         B = self.B
         with torch.cuda.device(self.eng.device):
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(s["ev_done"])
-                lab = s["labels"][:B * nmax].view(B, nmax)
-                idx = s["indices"][:B * nmax * 2].view(B, nmax, 2)
+                lab = s["labels"][:total]
+                idx = s["indices"][:total * 2].view(total, 2)
                 summ = s["summary"][:B * kmax * 8].view(B, kmax, 8)
-                if nmax:
-                    lab.copy_(res.labels[:, :nmax], non_blocking=True)
-                    idx.copy_(res.indices[:, :nmax], non_blocking=True)
+                for b in range(B):
+                    n, o = int(nv[b]), int(offsets[b])
+                    if n:
+                        lab[o:o + n].copy_(res.labels[b, :n], non_blocking=True)
+                        idx[o:o + n].copy_(res.indices[b, :n], non_blocking=True)
                 if kmax:
                     summ.copy_(res.summary[:, :kmax], non_blocking=True)
                 s["ev_d2h"].record(self.d2h)
@@ -485,4 +492,4 @@ class HostFlowPipeline:
         self.d2h_bytes = counts.nbytes + lab.numel() * 4 + idx.numel() * 4 + summ.numel() * 8
         s["res"] = None
         s["busy"] = False
-        return counts[0], counts[1], lab.numpy(), idx.numpy(), summ.numpy()
+        return counts[0], counts[1], offsets, lab.numpy(), idx.numpy(), summ.numpy()
