@@ -211,7 +211,9 @@ def run_ours(args):
 
     H = W = args.size
     B = args.batch
-    eng = Engine(local)
+    S = max(1, args.streams)
+    engines = [Engine(local, isolated=S > 1) for _ in range(S)]
+    eng = engines[0]
     params = farneback_params(**FB)
     px = py = 0.1
     # resident input pool: each rank owns a disjoint slice of the pair index space
@@ -221,14 +223,19 @@ def run_ours(args):
     next_pin = torch.from_numpy(next_h).pin_memory()
     prev_d = prev_pin.cuda(non_blocking=True)
     next_d = next_pin.cuda(non_blocking=True)
-    flow_buf = torch.empty((B, H, W, 2), dtype=torch.float32, device="cuda")
+    flow_bufs = [torch.empty((B, H, W, 2), dtype=torch.float32, device="cuda") for _ in range(S)]
+    flow_buf = flow_bufs[0]
     torch.cuda.synchronize()
     n_batches = n_pool // B
 
     def step(i):
+        # consecutive steps alternate between the engines (streams): the latency-bound clustering
+        # kernels of one batch overlap the flow kernels of the next
         s = (i % n_batches) * B
-        return eng.flow_pipeline(prev_d[s:s + B], next_d[s:s + B], px, py, ALPHA_CONT, EPS, MIN_SAMPLES, params,
-                                 cap=args.cap, max_clusters=args.max_clusters, keep_flow=False, flow_buf=flow_buf)
+        e = engines[i % S]
+        return e.flow_pipeline(prev_d[s:s + B], next_d[s:s + B], px, py, ALPHA_CONT, EPS, MIN_SAMPLES, params,
+                               cap=args.cap, max_clusters=args.max_clusters, keep_flow=False,
+                               flow_buf=flow_bufs[i % S])
 
     def barrier():
         torch.cuda.synchronize()
@@ -243,21 +250,33 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    eng.profile(True)
-    eng.profile_reset()
-    launches0 = eng.launch_count()
+    for e in engines:
+        e.profile(True)
+        e.profile_reset()
+    launches0 = sum(e.launch_count() for e in engines)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with eng.on_stream():
-        ev0.record()
+    main_stream = torch.cuda.current_stream()
+    ev0.record(main_stream)
+    for e in engines:
+        e.stream.wait_event(ev0)
     for i in range(args.steps):
         res = step(args.warmup + i)
-    with eng.on_stream():
-        ev1.record()
+    for e in engines:
+        main_stream.wait_stream(e.stream)
+    ev1.record(main_stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - launches0
-    prof = eng.profile_read()
-    eng.profile(False)
+    launches = sum(e.launch_count() for e in engines) - launches0
+    prof = None
+    for e in engines:
+        p = e.profile_read()
+        e.profile(False)
+        if prof is None:
+            prof = p
+        else:
+            for k in prof:
+                prof[k]["ms"] += p[k]["ms"]
+                prof[k]["launches"] += p[k]["launches"]
     clocks = sampler.stop() if rank == 0 else None
     n_valid_mean = float(res.n_valid.float().mean().item())
     n_clusters_mean = float(res.n_clusters.float().mean().item())
@@ -355,7 +374,8 @@ def run_ours(args):
                                               f"{rounds}, cv2 single-threaded each), {wall:.1f} s wall, "
                                               "oracle/reference_port.flow_to_clusters"}
         print(json.dumps(line), flush=True)
-    eng.close()
+    for e in engines:
+        e.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -374,6 +394,7 @@ def main():
     ap.add_argument("--max-clusters", type=int, default=1024)
     ap.add_argument("--cpu-rounds", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--streams", type=int, default=1, help="engines (streams) per GPU that alternate over the steps")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -347,27 +348,46 @@ template <typename SrcT, int N>
 __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp(const SrcT* __restrict__ src, float* __restrict__ R,
                                                              int w, int h, int imgs_per_array, PolyCoef pc) {
     constexpr int RW = P0_TX + 2 * N, RH = P0_TY + 2 * N;  // blurred-image region
-    constexpr int SWS = RW + 2, SHS = RH + 2;              // raw frame region (one more pixel each side)
+    constexpr int OX = (N + 1 + 3) & ~3;                   // raw region starts OX columns left of the tile (x4)
+    constexpr int NWD = (P0_TX + OX + N + 1 + 3) / 4;      // 4-pixel words per raw row
+    constexpr int SWS = NWD * 4 + 4, SHS = RH + 2;         // raw frame region (padded stride, 16-byte aligned)
     constexpr int RWP = (RW + 3) & ~3;                     // r-array row stride, float4-aligned
-    __shared__ float sS[SHS * SWS];
+    __shared__ __align__(16) float sS[SHS * SWS];
     __shared__ float sI[RH * RW];
     __shared__ __align__(16) float sr[3][P0_TY * RWP];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * P0_TX, y0 = blockIdx.y * P0_TY, b = blockIdx.z;
+    const int ox = x0 - OX, oy = y0 - N - 1;
     const size_t plane = static_cast<size_t>(w) * h;
     const SrcT* sb = src + b * plane;
-    // raw frame, reflected at the image border
-    for (int i = tid; i < SHS * SWS; i += P0_THREADS) {
-        const int yy = i / SWS, xx = i - yy * SWS;
-        const int gy = reflect101(y0 - N - 1 + yy, h), gx = reflect101(x0 - N - 1 + xx, w);
-        sS[i] = load_px(sb + static_cast<size_t>(gy) * w + gx);
+    // raw frame -> shared.  Tiles whose raw region lies inside the image (all but the border ring)
+    // move 4 pixels per load; border tiles reflect (BORDER_REFLECT_101) pixel by pixel.
+    if (ox >= 0 && ox + NWD * 4 <= w && oy >= 0 && oy + SHS <= h && (w & 3) == 0) {
+        for (int i = tid; i < SHS * NWD; i += P0_THREADS) {
+            const int yy = i / NWD, wd = i - yy * NWD;
+            const SrcT* p = sb + static_cast<size_t>(oy + yy) * w + ox + wd * 4;
+            float4 v;
+            if (sizeof(SrcT) == 1) {
+                const uchar4 u = *reinterpret_cast<const uchar4*>(p);
+                v = make_float4(u.x, u.y, u.z, u.w);
+            } else {
+                v = *reinterpret_cast<const float4*>(p);
+            }
+            *reinterpret_cast<float4*>(sS + yy * SWS + wd * 4) = v;
+        }
+    } else {
+        for (int i = tid; i < SHS * NWD * 4; i += P0_THREADS) {
+            const int yy = i / (NWD * 4), xx = i - yy * (NWD * 4);
+            const int gy = reflect101(oy + yy, h), gx = reflect101(ox + xx, w);
+            sS[yy * SWS + xx] = load_px(sb + static_cast<size_t>(gy) * w + gx);
+        }
     }
     __syncthreads();
     // blurred image at replicate-clamped coordinates (what polyExp's border handling reads)
     for (int i = tid; i < RH * RW; i += P0_THREADS) {
         const int yy = i / RW, xx = i - yy * RW;
         const int gy = min(max(y0 - N + yy, 0), h - 1), gx = min(max(x0 - N + xx, 0), w - 1);
-        const float* c = sS + (gy - (y0 - N - 1)) * SWS + (gx - (x0 - N - 1));
+        const float* c = sS + (gy - oy) * SWS + (gx - ox);
         // rows first (f32), then columns, like the separable filter
         const float t0 = 0.25f * c[-SWS - 1] + 0.5f * c[-SWS] + 0.25f * c[-SWS + 1];
         const float t1 = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
@@ -468,13 +488,15 @@ __global__ void __launch_bounds__(128) k_upsample_flow(const float2* __restrict_
     const float2* p = fin + static_cast<size_t>(b) * hi * wi;
     float2 a = p[static_cast<size_t>(sy) * wi + sx], bb = p[static_cast<size_t>(sy) * wi + sx1];
     float2 c = p[static_cast<size_t>(sy1) * wi + sx], d = p[static_cast<size_t>(sy1) * wi + sx1];
-    // horizontal pass rounded to f32, then vertical, as cv::resize does
-    float t0x = static_cast<float>((1.0 - fx) * a.x + fx * bb.x), t0y = static_cast<float>((1.0 - fx) * a.y + fx * bb.y);
-    float t1x = static_cast<float>((1.0 - fx) * c.x + fx * d.x), t1y = static_cast<float>((1.0 - fx) * c.y + fx * d.y);
-    float vx = static_cast<float>((1.0 - fy) * t0x + fy * t1x), vy = static_cast<float>((1.0 - fy) * t0y + fy * t1y);
+    // tap index / fraction in fp64 (they decide which texels are read); the interpolation itself in
+    // f32 — horizontal pass rounded to f32, then vertical, as cv::resize does
+    const float gx1 = static_cast<float>(fx), gx0 = 1.f - gx1, gy1 = static_cast<float>(fy), gy0 = 1.f - gy1;
+    const float t0x = gx0 * a.x + gx1 * bb.x, t0y = gx0 * a.y + gx1 * bb.y;
+    const float t1x = gx0 * c.x + gx1 * d.x, t1y = gx0 * c.y + gx1 * d.y;
+    const float fmul = static_cast<float>(mul);
     float2 o;
-    o.x = static_cast<float>(static_cast<double>(vx) * mul);
-    o.y = static_cast<float>(static_cast<double>(vy) * mul);
+    o.x = (gy0 * t0x + gy1 * t1x) * fmul;
+    o.y = (gy0 * t0y + gy1 * t1y) * fmul;
     fout[(static_cast<size_t>(b) * ho + y) * wo + x] = o;
 }
 
@@ -527,6 +549,7 @@ __device__ __forceinline__ void m_gather(const RView& r0, const RView& r1, int w
     }
 }
 
+template <bool BORDER = true>
 __device__ __forceinline__ void m_finish(const MTaps& T, int w, int h, int x, int y, float M[5]) {
     const float dx = T.dx, dy = T.dy;
     float r2, r3, r4, r5, r6;
@@ -550,7 +573,7 @@ __device__ __forceinline__ void m_finish(const MTaps& T, int w, int h, int x, in
     r3 = (T.q[1] - r3) * 0.5f;
     r2 += r4 * dy + r6 * dx;
     r3 += r6 * dy + r5 * dx;
-    if (x < 5 || x >= w - 5 || y < 5 || y >= h - 5) {
+    if (BORDER && (x < 5 || x >= w - 5 || y < 5 || y >= h - 5)) {
         float sc = (x < 5 ? c_border[x] : 1.f) * (x >= w - 5 ? c_border[w - 1 - x] : 1.f) *
                    (y < 5 ? c_border[y] : 1.f) * (y >= h - 5 ? c_border[h - 1 - y] : 1.f);
         r2 *= sc, r3 *= sc, r4 *= sc, r5 *= sc, r6 *= sc;
@@ -746,43 +769,77 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter_w(const float* __restric
             gy = min(max(y0 - M + yy, 0), h - 1);
             so = yy * SW + xx;
         };
-        if (FUSED) {
-            int gxa, gya, soa, gxb, gyb, sob;
-            float2 fa = make_float2(0.f, 0.f), fbv = fa;
-            int ia = tid, ib = tid + NT;
-            if (ia < NPIX) {
-                locate(ia, gxa, gya, soa);
-                fa = fb[static_cast<size_t>(gya) * w + gxa];
+        if (FUSED && MINB >= 3) {
+            // one pixel per trip (fewer live registers -> one more resident CTA); next flow prefetched
+            int gx = 0, gy = 0, so = 0;
+            float2 f = make_float2(0.f, 0.f);
+            int i = tid;
+            if (i < NPIX) {
+                locate(i, gx, gy, so);
+                f = fb[static_cast<size_t>(gy) * w + gx];
             }
-            if (ib < NPIX) {
-                locate(ib, gxb, gyb, sob);
-                fbv = fb[static_cast<size_t>(gyb) * w + gxb];
-            }
-            for (; ia < NPIX; ia += 2 * NT, ib += 2 * NT) {
-                const bool has_b = ib < NPIX;
-                MTaps Ta, Tb;
-                m_gather(R0b, R1b, w, h, gxa, gya, fa, Ta);
-                if (has_b) m_gather(R0b, R1b, w, h, gxb, gyb, fbv, Tb);
-                // prefetch the next trip's flow while these gathers are in flight
-                const int cgxa = gxa, cgya = gya, csoa = soa, cgxb = gxb, cgyb = gyb, csob = sob;
-                if (ia + 2 * NT < NPIX) {
-                    locate(ia + 2 * NT, gxa, gya, soa);
-                    fa = fb[static_cast<size_t>(gya) * w + gxa];
-                }
-                if (ib + 2 * NT < NPIX) {
-                    locate(ib + 2 * NT, gxb, gyb, sob);
-                    fbv = fb[static_cast<size_t>(gyb) * w + gxb];
+            for (; i < NPIX; i += NT) {
+                MTaps Ta;
+                m_gather(R0b, R1b, w, h, gx, gy, f, Ta);
+                const int cgx = gx, cgy = gy, cso = so;
+                if (i + NT < NPIX) {
+                    locate(i + NT, gx, gy, so);
+                    f = fb[static_cast<size_t>(gy) * w + gx];
                 }
                 float Mv[5];
-                m_finish(Ta, w, h, cgxa, cgya, Mv);
+                m_finish(Ta, w, h, cgx, cgy, Mv);
 #pragma unroll
-                for (int c = 0; c < 5; ++c) sM[c * RH * SW + csoa] = Mv[c];
-                if (has_b) {
-                    m_finish(Tb, w, h, cgxb, cgyb, Mv);
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) sM[c * RH * SW + csob] = Mv[c];
-                }
+                for (int c = 0; c < 5; ++c) sM[c * RH * SW + cso] = Mv[c];
             }
+        } else if (FUSED) {
+            // 2-D mapping: LW lanes along x, the thread walks the region in (LW, LH) strides, so
+            // coordinates are adds; tiles that touch neither the image border nor its 5-px
+            // attenuation band (the common case) skip every clamp and the border test.
+            constexpr int LW = 16, LH = NT / LW;
+            constexpr int NI = (RW + LW - 1) / LW, NJ = (RH + LH - 1) / LH;
+            const int tx = tid % LW, ty = tid / LW;
+            const bool interior = x0 - M >= 5 && x0 - M + RW <= w - 5 && y0 - M >= 5 && y0 - M + RH <= h - 5;
+            auto body = [&](auto interior_tag) {
+                constexpr bool INT = decltype(interior_tag)::value;
+                for (int j = 0; j < NJ; ++j) {
+                    const int yy = ty + j * LH;
+                    if (yy >= RH) break;
+                    const int gy = INT ? y0 - M + yy : min(max(y0 - M + yy, 0), h - 1);
+                    const float2* frow = fb + static_cast<size_t>(gy) * w;
+                    float2 f[NI];
+                    int gxs[NI];
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        const int xx = tx + i * LW;
+                        gxs[i] = INT ? x0 - M + xx : min(max(x0 - M + xx, 0), w - 1);
+                        if (xx < RW) f[i] = frow[gxs[i]];
+                    }
+                    float* srow = sM + yy * SW + tx;
+#pragma unroll
+                    for (int i = 0; i < NI; i += 2) {
+                        const bool has_a = tx + i * LW < RW;
+                        const bool has_b = i + 1 < NI && tx + (i + 1) * LW < RW;
+                        MTaps Ta, Tb;
+                        if (has_a) m_gather(R0b, R1b, w, h, gxs[i], gy, f[i], Ta);
+                        if (has_b) m_gather(R0b, R1b, w, h, gxs[i + 1 < NI ? i + 1 : i], gy, f[i + 1 < NI ? i + 1 : i], Tb);
+                        float Mv[5];
+                        if (has_a) {
+                            m_finish<!INT>(Ta, w, h, gxs[i], gy, Mv);
+#pragma unroll
+                            for (int c = 0; c < 5; ++c) srow[c * RH * SW + i * LW] = Mv[c];
+                        }
+                        if (has_b) {
+                            m_finish<!INT>(Tb, w, h, gxs[i + 1 < NI ? i + 1 : i], gy, Mv);
+#pragma unroll
+                            for (int c = 0; c < 5; ++c) srow[c * RH * SW + (i + 1) * LW] = Mv[c];
+                        }
+                    }
+                }
+            };
+            if (interior)
+                body(std::true_type{});
+            else
+                body(std::false_type{});
         } else {
             for (int i = tid; i < NPIX; i += NT) {
                 int gx, gy, so;
@@ -834,28 +891,31 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter_w(const float* __restric
 //   4. 2x2 solve of the WIN finished rows from sOld -> flow; then sOld / sNew swap roles.
 // Every output is still a sum of exactly its own window's values (no running sums).
 // ------------------------------------------------------------------------------------
-template <int TX, int WIN, int NT>
+template <int TX, int WIN, int NT, int SEGS>
 struct FlowMarch {
     static constexpr int M = WIN / 2;
     static constexpr int RW = TX + 2 * M;
     static constexpr int SWT = RW | 1;   // sMt row stride (odd)
     static constexpr int SWH = TX | 1;   // sOld / sNew row stride (odd)
     static constexpr int GROUP = WIN + 1;  // outputs per horizontal item
+    static constexpr int ROWS = SEGS * WIN;  // rows of M evaluated per step
     static_assert(TX % GROUP == 0, "TX must be a multiple of WIN + 1");
-    static constexpr size_t SMEM = static_cast<size_t>(5) * WIN * (SWT + 2 * SWH) * sizeof(float);
+    static constexpr size_t SMEM = static_cast<size_t>(5) * (ROWS * SWT + 2 * WIN * SWH) * sizeof(float);
 };
 
-template <int TX, int WIN, int NT, int MINB>
+// SEGS segments of WIN rows are evaluated per step (one long gather phase per barrier, like a
+// tile), then finished one segment at a time.
+template <int TX, int WIN, int NT, int MINB, int SEGS>
 __global__ void __launch_bounds__(NT, MINB) k_flow_iter_march(const float* __restrict__ R0,
                                                               const float* __restrict__ R1,
                                                               const float2* __restrict__ flow_in,
                                                               float2* __restrict__ flow_out, int w, int h,
                                                               int band_rows, float norm) {
-    using T = FlowMarch<TX, WIN, NT>;
-    constexpr int M = T::M, RW = T::RW, SWT = T::SWT, SWH = T::SWH, GROUP = T::GROUP;
+    using T = FlowMarch<TX, WIN, NT, SEGS>;
+    constexpr int M = T::M, RW = T::RW, SWT = T::SWT, SWH = T::SWH, GROUP = T::GROUP, ROWS = T::ROWS;
     extern __shared__ float smem[];
-    float* sMt = smem;                      // [5][WIN][SWT]
-    float* sA = sMt + 5 * WIN * SWT;        // [5][WIN][SWH]
+    float* sMt = smem;                      // [5][ROWS][SWT]
+    float* sA = sMt + 5 * ROWS * SWT;       // [5][WIN][SWH]
     float* sB = sA + 5 * WIN * SWH;
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TX, b = blockIdx.z;
@@ -868,11 +928,12 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter_march(const float* __res
     float* sOld = sA;   // suffix sums of the previous segment (horizontally summed)
     float* sNew = sB;
     const int n_seg = (r1 - r0 + WIN - 1) / WIN + 1;    // segment 0 only warms up
-    for (int seg = 0; seg < n_seg; ++seg) {
-        const int row0 = r0 - M + seg * WIN;            // first image row of this segment (may be < 0)
-        // ---- 1. M for the segment (rows / columns replicate-clamped), 2 pixels per trip ----------
+    for (int seg0 = 0; seg0 < n_seg; seg0 += SEGS) {
+        const int row0 = r0 - M + seg0 * WIN;           // first image row of this step (may be < 0)
+        const int rows_here = min(SEGS, n_seg - seg0) * WIN;
+        // ---- 1. M for the step's rows (rows / columns replicate-clamped), 2 pixels per trip -------
         {
-            constexpr int NPIX = WIN * RW;
+            const int NPIX = rows_here * RW;
             auto locate = [&](int i, int& gx, int& gy, int& so) {
                 const int yy = i / RW, xx = i - yy * RW;
                 gx = min(max(x0 - M + xx, 0), w - 1);
@@ -907,74 +968,79 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter_march(const float* __res
                 float Mv[5];
                 m_finish(Ta, w, h, cgxa, cgya, Mv);
 #pragma unroll
-                for (int c = 0; c < 5; ++c) sMt[c * WIN * SWT + csoa] = Mv[c];
+                for (int c = 0; c < 5; ++c) sMt[c * ROWS * SWT + csoa] = Mv[c];
                 if (has_b) {
                     m_finish(Tb, w, h, cgxb, cgyb, Mv);
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) sMt[c * WIN * SWT + csob] = Mv[c];
+                    for (int c = 0; c < 5; ++c) sMt[c * ROWS * SWT + csob] = Mv[c];
                 }
             }
         }
         __syncthreads();
-        // ---- 2. horizontal sums: item = (group of GROUP outputs, channel, row) --------------------
-        for (int i = tid; i < (TX / GROUP) * 5 * WIN; i += NT) {
-            const int g = i / (5 * WIN), cr = i - g * (5 * WIN);       // cr = c * WIN + row
-            const float* src = sMt + cr * SWT + g * GROUP;
-            float* dst = sNew + cr * SWH + g * GROUP;
-            float S[WIN];
+        for (int ss = 0; ss < SEGS && seg0 + ss < n_seg; ++ss) {
+            const int seg = seg0 + ss;
+            // ---- 2. horizontal sums: item = (group of GROUP outputs, channel, row) ----------------
+            for (int i = tid; i < (TX / GROUP) * 5 * WIN; i += NT) {
+                const int g = i / (5 * WIN), cr = i - g * (5 * WIN);       // cr = c * WIN + row
+                const int c = cr / WIN, j0 = cr - c * WIN;
+                const float* src = sMt + (c * ROWS + ss * WIN + j0) * SWT + g * GROUP;
+                float* dst = sNew + cr * SWH + g * GROUP;
+                float S[WIN];
 #pragma unroll
-            for (int j = 0; j < WIN; ++j) S[j] = src[j];
+                for (int j = 0; j < WIN; ++j) S[j] = src[j];
 #pragma unroll
-            for (int j = WIN - 2; j >= 0; --j) S[j] += S[j + 1];
-            dst[0] = S[0];
-            float P = 0.f;
-#pragma unroll
-            for (int j = 0; j < WIN; ++j) {
-                P += src[WIN + j];
-                dst[j + 1] = (j + 1 < WIN ? S[j + 1] : 0.f) + P;
-            }
-        }
-        __syncthreads();
-        // ---- 3. vertical: item = (channel, column) ------------------------------------------------
-        for (int i = tid; i < 5 * TX; i += NT) {
-            const int c = i / TX, x = i - c * TX;
-            float* pn = sNew + c * WIN * SWH + x;
-            float* po = sOld + c * WIN * SWH + x;
-            float v[WIN];
-#pragma unroll
-            for (int j = 0; j < WIN; ++j) v[j] = pn[j * SWH];
-            if (seg > 0) {
+                for (int j = WIN - 2; j >= 0; --j) S[j] += S[j + 1];
+                dst[0] = S[0];
                 float P = 0.f;
 #pragma unroll
-                for (int j = 1; j < WIN; ++j) {
-                    P += v[j - 1];
-                    po[j * SWH] += P;   // window starting at row j of the previous segment
+                for (int j = 0; j < WIN; ++j) {
+                    P += src[WIN + j];
+                    dst[j + 1] = (j + 1 < WIN ? S[j + 1] : 0.f) + P;
                 }
             }
+            __syncthreads();
+            // ---- 3. vertical: item = (channel, column) ---------------------------------------------
+            for (int i = tid; i < 5 * TX; i += NT) {
+                const int c = i / TX, x = i - c * TX;
+                float* pn = sNew + c * WIN * SWH + x;
+                float* po = sOld + c * WIN * SWH + x;
+                float v[WIN];
 #pragma unroll
-            for (int j = WIN - 2; j >= 0; --j) v[j] += v[j + 1];
+                for (int j = 0; j < WIN; ++j) v[j] = pn[j * SWH];
+                if (seg > 0) {
+                    float P = 0.f;
 #pragma unroll
-            for (int j = 0; j < WIN; ++j) pn[j * SWH] = v[j];
-        }
-        __syncthreads();
-        // ---- 4. solve the WIN rows finished by this step -------------------------------------------
-        if (seg > 0) {
-            const int out0 = r0 + (seg - 1) * WIN;     // image row of window j = 0
-            for (int i = tid; i < WIN * TX; i += NT) {
-                const int j = i / TX, x = i - j * TX;
-                const int gy = out0 + j, gx = x0 + x;
-                if (gy >= r1 || gx >= w) continue;
-                float g[5];
+                    for (int j = 1; j < WIN; ++j) {
+                        P += v[j - 1];
+                        po[j * SWH] += P;   // window starting at row j of the previous segment
+                    }
+                }
 #pragma unroll
-                for (int c = 0; c < 5; ++c) g[c] = sOld[(c * WIN + j) * SWH + x] * norm;
-                fo[static_cast<size_t>(gy) * w + gx] = solve_flow(g);
+                for (int j = WIN - 2; j >= 0; --j) v[j] += v[j + 1];
+#pragma unroll
+                for (int j = 0; j < WIN; ++j) pn[j * SWH] = v[j];
             }
+            __syncthreads();
+            // ---- 4. solve the WIN rows finished by this segment ---------------------------------------
+            if (seg > 0) {
+                const int out0 = r0 + (seg - 1) * WIN;     // image row of window j = 0
+                for (int i = tid; i < WIN * TX; i += NT) {
+                    const int j = i / TX, x = i - j * TX;
+                    const int gy = out0 + j, gx = x0 + x;
+                    if (gy >= r1 || gx >= w) continue;
+                    float g[5];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) g[c] = sOld[(c * WIN + j) * SWH + x] * norm;
+                    fo[static_cast<size_t>(gy) * w + gx] = solve_flow(g);
+                }
+            }
+            // the buffer just solved becomes the next sNew; its next write (step 2) must wait for
+            // the solve reads above
+            float* t = sOld;
+            sOld = sNew;
+            sNew = t;
+            if (SEGS > 1) __syncthreads();
         }
-        // the buffer just solved becomes the next step's sNew; the next write to it is behind
-        // the barrier after step 1
-        float* t = sOld;
-        sOld = sNew;
-        sNew = t;
     }
 }
 
@@ -1076,13 +1142,13 @@ int launch_flow_iter_w(datmo_ctx* h, const float* R0, const float* R1, const flo
     return DATMO_OK;
 }
 
-template <int TX, int NT, int MINB>
+template <int TX, int NT, int MINB, int SEGS>
 int launch_flow_iter_march(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, float* flow_out,
                            int w, int hh, int B, float norm) {
-    using T = FlowMarch<TX, 15, NT>;
+    using T = FlowMarch<TX, 15, NT, SEGS>;
     static bool attr_set = false;
     if (!attr_set) {
-        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter_march<TX, 15, NT, MINB>,
+        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter_march<TX, 15, NT, MINB, SEGS>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  static_cast<int>(T::SMEM)));
         attr_set = true;
@@ -1097,7 +1163,7 @@ int launch_flow_iter_march(datmo_ctx* h, const float* R0, const float* R1, const
     dim3 g(strips, bands, B);
     {
         LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
-        k_flow_iter_march<TX, 15, NT, MINB><<<g, NT, T::SMEM, h->stream>>>(
+        k_flow_iter_march<TX, 15, NT, MINB, SEGS><<<g, NT, T::SMEM, h->stream>>>(
             R0, R1, reinterpret_cast<const float2*>(flow_in), reinterpret_cast<float2*>(flow_out), w, hh, band_rows,
             norm);
     }
@@ -1114,11 +1180,12 @@ int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float
         // the reference's winsize 15 (and 14): compile-time window, tile picked from a small table
         static const int tile = flow_tile_choice();
         if (FUSED) {
-            if (tile == 10) return launch_flow_iter_march<64, 256, 2>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-            if (tile == 11) return launch_flow_iter_march<64, 192, 2>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-            if (tile == 12) return launch_flow_iter_march<64, 128, 4>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-            if (tile == 13) return launch_flow_iter_march<128, 256, 2>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-            if (tile == 14) return launch_flow_iter_march<32, 128, 4>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+            if (tile == 10) return launch_flow_iter_march<64, 256, 2, 1>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+            if (tile == 11) return launch_flow_iter_march<64, 256, 2, 2>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+            if (tile == 12) return launch_flow_iter_march<64, 256, 2, 3>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+            if (tile == 13) return launch_flow_iter_march<64, 256, 2, 4>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+            if (tile == 14) return launch_flow_iter_march<128, 256, 1, 2>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+            if (tile == 15) return launch_flow_iter_march<32, 256, 2, 4>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
         }
         switch (tile) {
             case 0: return launch_flow_iter_w<32, 32, 256, 4, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
@@ -1128,7 +1195,8 @@ int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float
             case 5: return launch_flow_iter_w<128, 16, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
             case 6: return launch_flow_iter_w<64, 32, 384, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
             case 7: return launch_flow_iter_w<64, 32, 512, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 8: return launch_flow_iter_w<32, 32, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 8: return launch_flow_iter_w<64, 64, 512, 1, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 9: return launch_flow_iter_w<128, 32, 512, 1, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
             default: return launch_flow_iter_w<64, 32, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
         }
     }

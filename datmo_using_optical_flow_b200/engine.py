@@ -53,7 +53,11 @@ class FlowPipelineResult:
 class Engine:
     """One per (device, stream); not thread-safe (same rule as the C handle)."""
 
-    def __init__(self, device: int | None = None):
+    def __init__(self, device: int | None = None, isolated: bool = False):
+        """isolated=True: the engine's stream is NOT ordered against the caller's current stream
+        (no wait_stream on entry / exit), so several engines can run concurrently on one GPU; the
+        caller then orders inputs / outputs itself (events or a synchronize)."""
+        self.isolated = isolated
         if not torch.cuda.is_available():
             raise _lib.DatmoLibraryError("no CUDA device: datmo_b200 has no CPU fallback")
         self.lib = _lib.load()
@@ -89,6 +93,10 @@ class Engine:
         ordered after the caller's current stream and before its later work."""
         with torch.cuda.device(self.device):
             outer = torch.cuda.current_stream()
+            if self.isolated or outer == self.stream:
+                with torch.cuda.stream(self.stream):
+                    yield
+                return
             self.stream.wait_stream(outer)
             with torch.cuda.stream(self.stream):
                 yield

@@ -110,7 +110,7 @@ def test_stage_upsample_flow(engine):
     f = rng.uniform(-3, 3, (36, 41, 2)).astype(np.float32)
     want = (fb.resize_linear(f, 120, 137).astype(np.float64) * (1 / 0.3)).astype(np.float32)
     got = host(engine.fb_upsample_flow(dev(f[None]), 120, 137, 1 / 0.3))[0]
-    assert np.abs(got - want).max() <= 1e-6
+    assert np.abs(got - want).max() <= 5e-6      # f32 interpolation of fp64-chosen taps
 
 
 @pytest.mark.parametrize("H,W,kw", [
