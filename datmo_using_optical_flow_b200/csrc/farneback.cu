@@ -9,8 +9,11 @@
 //     reads (k_pyr_h, k_pyr_v), instead of blurring the full-resolution frame;
 //   * polynomial expansion is one tiled kernel, both separable passes staged through
 //     shared memory (k_polyexp), for prev and next frames of the whole batch at once;
+//   * the finest layer's pyramid image + polynomial expansion is ONE kernel straight from the
+//     uint8 frame (k_pyr0_polyexp);
 //   * one flow iteration = updateMatrices + 5-channel box blur + 2x2 solve is ONE
-//     kernel (k_flow_iter<true>): the M field never exists in global memory;
+//     kernel (k_flow_iter_w for the reference's window, k_flow_iter otherwise): the M field
+//     never exists in global memory;
 //   * the 5-coefficient fields R0 / R1 are stored per array of B images as
 //     [B][h*w] float4 (coefficients 0..3) followed by [B][h*w] float (coefficient 4): a
 //     bilinear tap is one 16-byte + one 4-byte load instead of five scalar ones, and a warp
@@ -615,7 +618,7 @@ __global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict
 // ------------------------------------------------------------------------------------
 constexpr int FI_TX = 32, FI_TY = 32, FI_THREADS = 256;
 #ifndef DATMO_FI_TILE_DEFAULT
-#define DATMO_FI_TILE_DEFAULT 3
+#define DATMO_FI_TILE_DEFAULT 0
 #endif
 
 __device__ __forceinline__ float2 solve_flow(const float g[5]) {
@@ -875,175 +878,6 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter_w(const float* __restric
     }
 }
 
-// ------------------------------------------------------------------------------------
-// F5 + F6 fused, row-marching form (the default for winsize 14 / 15).
-//
-// A CTA owns a strip of TX columns and marches down a band of rows in steps of WIN rows.
-// Tiles pay the (TX+2m)(TY+2m)/(TX*TY) halo on the expensive part — the M gather — in both
-// directions; marching pays it only sideways (plus one WIN-1 row warm-up per band).
-// Per step, for the WIN new rows ("segment"):
-//   1. M for WIN x (TX+2m) pixels                                   -> sMt   (transient)
-//   2. horizontal window sums, one van Herk step per 16 outputs     -> sNew  [5][WIN][TX]
-//   3. vertical: a window starting at row j of the PREVIOUS segment is
-//        (suffix sum of the previous segment from j) + (prefix sum of the new one up to j-1);
-//      one thread per (column, channel) turns sOld (suffix sums) into the finished box sums
-//      in place and sNew into its own suffix sums in place
-//   4. 2x2 solve of the WIN finished rows from sOld -> flow; then sOld / sNew swap roles.
-// Every output is still a sum of exactly its own window's values (no running sums).
-// ------------------------------------------------------------------------------------
-template <int TX, int WIN, int NT, int SEGS>
-struct FlowMarch {
-    static constexpr int M = WIN / 2;
-    static constexpr int RW = TX + 2 * M;
-    static constexpr int SWT = RW | 1;   // sMt row stride (odd)
-    static constexpr int SWH = TX | 1;   // sOld / sNew row stride (odd)
-    static constexpr int GROUP = WIN + 1;  // outputs per horizontal item
-    static constexpr int ROWS = SEGS * WIN;  // rows of M evaluated per step
-    static_assert(TX % GROUP == 0, "TX must be a multiple of WIN + 1");
-    static constexpr size_t SMEM = static_cast<size_t>(5) * (ROWS * SWT + 2 * WIN * SWH) * sizeof(float);
-};
-
-// SEGS segments of WIN rows are evaluated per step (one long gather phase per barrier, like a
-// tile), then finished one segment at a time.
-template <int TX, int WIN, int NT, int MINB, int SEGS>
-__global__ void __launch_bounds__(NT, MINB) k_flow_iter_march(const float* __restrict__ R0,
-                                                              const float* __restrict__ R1,
-                                                              const float2* __restrict__ flow_in,
-                                                              float2* __restrict__ flow_out, int w, int h,
-                                                              int band_rows, float norm) {
-    using T = FlowMarch<TX, WIN, NT, SEGS>;
-    constexpr int M = T::M, RW = T::RW, SWT = T::SWT, SWH = T::SWH, GROUP = T::GROUP, ROWS = T::ROWS;
-    extern __shared__ float smem[];
-    float* sMt = smem;                      // [5][ROWS][SWT]
-    float* sA = sMt + 5 * ROWS * SWT;       // [5][WIN][SWH]
-    float* sB = sA + 5 * WIN * SWH;
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TX, b = blockIdx.z;
-    const int r0 = blockIdx.y * band_rows;              // first output row of this band
-    const int r1 = min(r0 + band_rows, h);              // one past the last
-    const size_t plane = static_cast<size_t>(w) * h;
-    const RView R0b = r_view(R0, gridDim.z, b, plane), R1b = r_view(R1, gridDim.z, b, plane);
-    const float2* fb = flow_in + static_cast<size_t>(b) * plane;
-    float2* fo = flow_out + static_cast<size_t>(b) * plane;
-    float* sOld = sA;   // suffix sums of the previous segment (horizontally summed)
-    float* sNew = sB;
-    const int n_seg = (r1 - r0 + WIN - 1) / WIN + 1;    // segment 0 only warms up
-    for (int seg0 = 0; seg0 < n_seg; seg0 += SEGS) {
-        const int row0 = r0 - M + seg0 * WIN;           // first image row of this step (may be < 0)
-        const int rows_here = min(SEGS, n_seg - seg0) * WIN;
-        // ---- 1. M for the step's rows (rows / columns replicate-clamped), 2 pixels per trip -------
-        {
-            const int NPIX = rows_here * RW;
-            auto locate = [&](int i, int& gx, int& gy, int& so) {
-                const int yy = i / RW, xx = i - yy * RW;
-                gx = min(max(x0 - M + xx, 0), w - 1);
-                gy = min(max(row0 + yy, 0), h - 1);
-                so = yy * SWT + xx;
-            };
-            int gxa = 0, gya = 0, soa = 0, gxb = 0, gyb = 0, sob = 0;
-            float2 fa = make_float2(0.f, 0.f), fbv = fa;
-            int ia = tid, ib = tid + NT;
-            if (ia < NPIX) {
-                locate(ia, gxa, gya, soa);
-                fa = fb[static_cast<size_t>(gya) * w + gxa];
-            }
-            if (ib < NPIX) {
-                locate(ib, gxb, gyb, sob);
-                fbv = fb[static_cast<size_t>(gyb) * w + gxb];
-            }
-            for (; ia < NPIX; ia += 2 * NT, ib += 2 * NT) {
-                const bool has_b = ib < NPIX;
-                MTaps Ta, Tb;
-                m_gather(R0b, R1b, w, h, gxa, gya, fa, Ta);
-                if (has_b) m_gather(R0b, R1b, w, h, gxb, gyb, fbv, Tb);
-                const int cgxa = gxa, cgya = gya, csoa = soa, cgxb = gxb, cgyb = gyb, csob = sob;
-                if (ia + 2 * NT < NPIX) {
-                    locate(ia + 2 * NT, gxa, gya, soa);
-                    fa = fb[static_cast<size_t>(gya) * w + gxa];
-                }
-                if (ib + 2 * NT < NPIX) {
-                    locate(ib + 2 * NT, gxb, gyb, sob);
-                    fbv = fb[static_cast<size_t>(gyb) * w + gxb];
-                }
-                float Mv[5];
-                m_finish(Ta, w, h, cgxa, cgya, Mv);
-#pragma unroll
-                for (int c = 0; c < 5; ++c) sMt[c * ROWS * SWT + csoa] = Mv[c];
-                if (has_b) {
-                    m_finish(Tb, w, h, cgxb, cgyb, Mv);
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) sMt[c * ROWS * SWT + csob] = Mv[c];
-                }
-            }
-        }
-        __syncthreads();
-        for (int ss = 0; ss < SEGS && seg0 + ss < n_seg; ++ss) {
-            const int seg = seg0 + ss;
-            // ---- 2. horizontal sums: item = (group of GROUP outputs, channel, row) ----------------
-            for (int i = tid; i < (TX / GROUP) * 5 * WIN; i += NT) {
-                const int g = i / (5 * WIN), cr = i - g * (5 * WIN);       // cr = c * WIN + row
-                const int c = cr / WIN, j0 = cr - c * WIN;
-                const float* src = sMt + (c * ROWS + ss * WIN + j0) * SWT + g * GROUP;
-                float* dst = sNew + cr * SWH + g * GROUP;
-                float S[WIN];
-#pragma unroll
-                for (int j = 0; j < WIN; ++j) S[j] = src[j];
-#pragma unroll
-                for (int j = WIN - 2; j >= 0; --j) S[j] += S[j + 1];
-                dst[0] = S[0];
-                float P = 0.f;
-#pragma unroll
-                for (int j = 0; j < WIN; ++j) {
-                    P += src[WIN + j];
-                    dst[j + 1] = (j + 1 < WIN ? S[j + 1] : 0.f) + P;
-                }
-            }
-            __syncthreads();
-            // ---- 3. vertical: item = (channel, column) ---------------------------------------------
-            for (int i = tid; i < 5 * TX; i += NT) {
-                const int c = i / TX, x = i - c * TX;
-                float* pn = sNew + c * WIN * SWH + x;
-                float* po = sOld + c * WIN * SWH + x;
-                float v[WIN];
-#pragma unroll
-                for (int j = 0; j < WIN; ++j) v[j] = pn[j * SWH];
-                if (seg > 0) {
-                    float P = 0.f;
-#pragma unroll
-                    for (int j = 1; j < WIN; ++j) {
-                        P += v[j - 1];
-                        po[j * SWH] += P;   // window starting at row j of the previous segment
-                    }
-                }
-#pragma unroll
-                for (int j = WIN - 2; j >= 0; --j) v[j] += v[j + 1];
-#pragma unroll
-                for (int j = 0; j < WIN; ++j) pn[j * SWH] = v[j];
-            }
-            __syncthreads();
-            // ---- 4. solve the WIN rows finished by this segment ---------------------------------------
-            if (seg > 0) {
-                const int out0 = r0 + (seg - 1) * WIN;     // image row of window j = 0
-                for (int i = tid; i < WIN * TX; i += NT) {
-                    const int j = i / TX, x = i - j * TX;
-                    const int gy = out0 + j, gx = x0 + x;
-                    if (gy >= r1 || gx >= w) continue;
-                    float g[5];
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) g[c] = sOld[(c * WIN + j) * SWH + x] * norm;
-                    fo[static_cast<size_t>(gy) * w + gx] = solve_flow(g);
-                }
-            }
-            // the buffer just solved becomes the next sNew; its next write (step 2) must wait for
-            // the solve reads above
-            float* t = sOld;
-            sOld = sNew;
-            sNew = t;
-            if (SEGS > 1) __syncthreads();
-        }
-    }
-}
-
 size_t flow_iter_smem(int m) {
     int RW = FI_TX + 2 * m, RH = FI_TY + 2 * m, SW = RW | 1;
     return static_cast<size_t>(5) * (RH + FI_TY) * SW * sizeof(float);
@@ -1142,62 +976,20 @@ int launch_flow_iter_w(datmo_ctx* h, const float* R0, const float* R1, const flo
     return DATMO_OK;
 }
 
-template <int TX, int NT, int MINB, int SEGS>
-int launch_flow_iter_march(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, float* flow_out,
-                           int w, int hh, int B, float norm) {
-    using T = FlowMarch<TX, 15, NT, SEGS>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter_march<TX, 15, NT, MINB, SEGS>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(T::SMEM)));
-        attr_set = true;
-    }
-    // bands: enough CTAs for ~2 waves of the machine, band height a multiple of the window
-    const int strips = ceil_div(w, TX);
-    const int want = 2 * h->sm_count * MINB;
-    int bands = std::max(1, std::min(ceil_div(hh, 15), ceil_div(want, strips * B)));
-    int band_rows = ceil_div(ceil_div(hh, bands), 15) * 15;
-    if (const char* e = getenv("DATMO_FI_BAND")) band_rows = std::max(15, atoi(e) / 15 * 15);
-    bands = ceil_div(hh, band_rows);
-    dim3 g(strips, bands, B);
-    {
-        LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
-        k_flow_iter_march<TX, 15, NT, MINB, SEGS><<<g, NT, T::SMEM, h->stream>>>(
-            R0, R1, reinterpret_cast<const float2*>(flow_in), reinterpret_cast<float2*>(flow_out), w, hh, band_rows,
-            norm);
-    }
-    DATMO_POST_LAUNCH(h);
-    return DATMO_OK;
-}
-
 template <bool FUSED>
 int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, const float* Min,
                      float* flow_out, int w, int hh, int B, int winsize) {
     int m = winsize / 2;
     float norm = static_cast<float>(1.0 / (static_cast<double>(winsize) * winsize));
     if (m == 7 && !getenv("DATMO_GENERIC_FLOW_ITER")) {
-        // the reference's winsize 15 (and 14): compile-time window, tile picked from a small table
+        // the reference's winsize 15 (and 14): compile-time window.  DATMO_FI_TILE selects the A/B
+        // alternatives measured in DESIGN.md §5 (1: 32x32 tile, one pixel per trip, 4 CTAs/SM;
+        // 2: 64x64 tile, 512 threads, 1 CTA/SM); all three land within 3 % of each other
         static const int tile = flow_tile_choice();
-        if (FUSED) {
-            if (tile == 10) return launch_flow_iter_march<64, 256, 2, 1>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-            if (tile == 11) return launch_flow_iter_march<64, 256, 2, 2>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-            if (tile == 12) return launch_flow_iter_march<64, 256, 2, 3>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-            if (tile == 13) return launch_flow_iter_march<64, 256, 2, 4>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-            if (tile == 14) return launch_flow_iter_march<128, 256, 1, 2>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-            if (tile == 15) return launch_flow_iter_march<32, 256, 2, 4>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-        }
         switch (tile) {
-            case 0: return launch_flow_iter_w<32, 32, 256, 4, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 2: return launch_flow_iter_w<64, 32, 512, 1, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 3: return launch_flow_iter_w<64, 32, 256, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 4: return launch_flow_iter_w<64, 16, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 5: return launch_flow_iter_w<128, 16, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 6: return launch_flow_iter_w<64, 32, 384, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 7: return launch_flow_iter_w<64, 32, 512, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 8: return launch_flow_iter_w<64, 64, 512, 1, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 9: return launch_flow_iter_w<128, 32, 512, 1, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            default: return launch_flow_iter_w<64, 32, 256, 3, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 1: return launch_flow_iter_w<32, 32, 256, 4, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            case 2: return launch_flow_iter_w<64, 64, 512, 1, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
+            default: return launch_flow_iter_w<64, 32, 256, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
         }
     }
     size_t smem = flow_iter_smem(m);

@@ -213,3 +213,29 @@ def test_full_size_1024_properties(engine):
     want = _cv(a, b, **REF)
     d = np.abs(f1[0] - want)
     assert d.max() <= 1e-3 and d.mean() <= 1e-5, (d.max(), d.mean())
+
+
+def test_cfg2_five_layer_pyramid_800(engine):
+    """BASELINE configs[1]: 800x800, pyr_scale 0.5 x 5 levels (layers 50..800), winsize 15."""
+    p = dict(REF, pyr_scale=0.5, levels=5)
+    assert engine.farneback_layers(800, 800, farneback_params(**p)) == [(50, 50), (100, 100), (200, 200), (400, 400), (800, 800)]
+    a, b = synth.textured_pair(21, 800, 800, shift=(-3, 2))
+    d = np.abs(host(engine.farneback(dev(a), dev(b), farneback_params(**p)))[0] - _cv(a, b, **p))
+    assert d.max() <= 1e-3 and d.mean() <= 1e-5, (d.max(), d.mean())
+    a, b = synth.bev_pair(22, 800, 800)
+    d = np.abs(host(engine.farneback(dev(a), dev(b), farneback_params(**p)))[0] - _cv(a, b, **p)).max(axis=2)
+    # conditioning floor of this frame: the fp64 numpy oracle differs from cv2 by max 1.89e-2 (one
+    # texture-free pixel), cv2 from itself under a 1-ulp input perturbation by max 1.07e-2
+    assert d.mean() <= 2e-5 and np.quantile(d, 0.999) <= 1e-3 and d.max() <= 3e-2, (d.mean(), d.max())
+
+
+def test_cfg4_high_res_2048_poly7_ten_iterations(engine):
+    """BASELINE configs[3]: 2048x2048, poly_n 7, poly_sigma 1.5, 10 iterations (4 layers, ksize up to 91)."""
+    p = dict(REF, poly_n=7, poly_sigma=1.5, iterations=10)
+    assert engine.farneback_layers(2048, 2048, farneback_params(**p)) == [(55, 55), (184, 184), (614, 614), (2048, 2048)]
+    a, b = synth.textured_pair(23, 2048, 2048, shift=(2, 3))
+    got = host(engine.farneback(dev(a), dev(b), farneback_params(**p)))[0]
+    d = np.abs(got - _cv(a, b, **p))
+    assert d.max() <= 1e-3 and d.mean() <= 1e-5, (d.max(), d.mean())
+    core = got[128:-128, 128:-128]
+    assert abs(np.median(core[..., 0]) - 3) < 0.05 and abs(np.median(core[..., 1]) - 2) < 0.05
