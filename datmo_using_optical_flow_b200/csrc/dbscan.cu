@@ -337,24 +337,51 @@ __global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx,
     }
 }
 
-// flatten + mark roots
-__global__ void __launch_bounds__(256) k_flatten(const uint8_t* __restrict__ state, int64_t n,
-                                                 int32_t* __restrict__ parent, uint8_t* __restrict__ is_root) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+// Flatten: point every core cell straight at its root (parent is -1 for anything that is not a
+// core cell, so the forest alone says who takes part).  Four cells per thread through one
+// 16-byte load; MARK_ROOTS additionally writes the root flags the final label scan consumes.
+template <bool MARK_ROOTS>
+__global__ void __launch_bounds__(256) k_flatten(int64_t n, int32_t* __restrict__ parent,
+                                                 uint8_t* __restrict__ is_root) {
+    const int64_t i4 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
     const int b = blockIdx.y;
-    if (i >= n) return;
-    const size_t base = static_cast<size_t>(b) * n;
-    uint8_t root = 0;
-    if (state[base + i] == 2) {
-        int a = static_cast<int>(i);
-        int32_t* par = parent + base;
-        int p = par[a];
-        while (p != par[p]) p = par[p];
-        // all unions are finished (previous kernel), so this write cannot race with a link
-        par[a] = p;
-        root = p == a;
+    if (i4 >= n) return;
+    int32_t* par = parent + static_cast<size_t>(b) * n;
+    int p[4];
+    const bool vec = i4 + 3 < n && ((static_cast<size_t>(b) * n) & 3) == 0;
+    if (vec) {
+        const int4 v = *reinterpret_cast<const int4*>(par + i4);
+        p[0] = v.x, p[1] = v.y, p[2] = v.z, p[3] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = i4 + k < n ? par[i4 + k] : -1;
     }
-    is_root[base + i] = root;
+    uint8_t root[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (p[k] < 0) continue;
+        const int a = static_cast<int>(i4) + k;
+        int r = p[k];
+        // all unions are finished (previous kernel), so roots are fixed points; concurrent
+        // compressions by other threads only replace a parent by one of its ancestors
+        while (true) {
+            const int up = par[r];
+            if (up == r) break;
+            r = up;
+        }
+        if (r != p[k]) par[a] = r;
+        root[k] = r == a;
+    }
+    if (MARK_ROOTS) {
+        uint8_t* dst = is_root + static_cast<size_t>(b) * n + i4;
+        if (vec) {
+            *reinterpret_cast<uchar4*>(dst) = make_uchar4(root[0], root[1], root[2], root[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i4 + k < n) dst[k] = root[k];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_labels(const float* __restrict__ vx, const float* __restrict__ vy,
@@ -551,7 +578,7 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
         k_core<<<g, 256, 0, h->stream>>>(vx_f, vy_f, valid, H, W, r, eps2, min_samples, state, parent);
     }
     DATMO_POST_LAUNCH(h);
-    dim3 gf(static_cast<unsigned>(ceil_div64(n, 256)), batch);
+    dim3 gf(static_cast<unsigned>(ceil_div64(n, 1024)), batch);
     if (r >= 1) {
         {
             LaunchScope ls(h, dbg_tag(2));
@@ -560,7 +587,7 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
         DATMO_POST_LAUNCH(h);
         {
             LaunchScope ls(h, dbg_tag(3));
-            k_flatten<<<gf, 256, 0, h->stream>>>(state, n, parent, is_root);
+            k_flatten<false><<<gf, 256, 0, h->stream>>>(n, parent, is_root);
         }
         DATMO_POST_LAUNCH(h);
         {
@@ -571,7 +598,7 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
         if (r > 1) {
             {
                 LaunchScope ls(h, dbg_tag(3));
-                k_flatten<<<gf, 256, 0, h->stream>>>(state, n, parent, is_root);
+                k_flatten<false><<<gf, 256, 0, h->stream>>>(n, parent, is_root);
             }
             DATMO_POST_LAUNCH(h);
             {
@@ -583,7 +610,7 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
     }
     {
         LaunchScope ls(h, dbg_tag(3));
-        k_flatten<<<gf, 256, 0, h->stream>>>(state, n, parent, is_root);
+        k_flatten<true><<<gf, 256, 0, h->stream>>>(n, parent, is_root);
     }
     DATMO_POST_LAUNCH(h);
     int32_t* ncl_out = n_clusters ? n_clusters : ncl;
