@@ -486,19 +486,37 @@ __global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__
     const unsigned peers = __match_any_sync(0xffffffffu, lab);
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
-    unsigned long long sr = 0, sc = 0, srr = 0, src = 0, scc = 0;
-    double svx = 0.0, svy = 0.0;
-    unsigned rem = peers;
-    while (__any_sync(0xffffffffu, rem != 0)) {
-        const int src_lane = rem ? __ffs(rem) - 1 : 0;
-        const unsigned long long tr = __shfl_sync(0xffffffffu, r, src_lane);
-        const unsigned long long tc = __shfl_sync(0xffffffffu, c, src_lane);
-        const double tvx = __shfl_sync(0xffffffffu, fvx, src_lane);
-        const double tvy = __shfl_sync(0xffffffffu, fvy, src_lane);
-        if (rem) {
-            sr += tr, sc += tc, srr += tr * tr, src += tr * tc, scc += tc * tc;
-            svx += tvx, svy += tvy;
-            rem &= rem - 1;
+    unsigned long long sr, sc, srr, src, scc;
+    double svx, svy;
+    if (peers == 0xffffffffu) {
+        // the usual case — the whole warp sits in one cluster: butterfly reduction
+        sr = r, sc = c, srr = r * r, src = r * c, scc = c * c;
+        svx = fvx, svy = fvy;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            sc += __shfl_xor_sync(0xffffffffu, sc, o);
+            srr += __shfl_xor_sync(0xffffffffu, srr, o);
+            src += __shfl_xor_sync(0xffffffffu, src, o);
+            scc += __shfl_xor_sync(0xffffffffu, scc, o);
+            svx += __shfl_xor_sync(0xffffffffu, svx, o);
+            svy += __shfl_xor_sync(0xffffffffu, svy, o);
+        }
+    } else {
+        sr = sc = srr = src = scc = 0;
+        svx = svy = 0.0;
+        unsigned rem = peers;
+        while (__any_sync(0xffffffffu, rem != 0)) {
+            const int src_lane = rem ? __ffs(rem) - 1 : 0;
+            const unsigned long long tr = __shfl_sync(0xffffffffu, r, src_lane);
+            const unsigned long long tc = __shfl_sync(0xffffffffu, c, src_lane);
+            const double tvx = __shfl_sync(0xffffffffu, fvx, src_lane);
+            const double tvy = __shfl_sync(0xffffffffu, fvy, src_lane);
+            if (rem) {
+                sr += tr, sc += tc, srr += tr * tr, src += tr * tc, scc += tc * tc;
+                svx += tvx, svy += tvy;
+                rem &= rem - 1;
+            }
         }
     }
     if (lane == leader && lab >= 0) {
