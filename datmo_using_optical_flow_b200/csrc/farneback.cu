@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict
 // ------------------------------------------------------------------------------------
 constexpr int FI_TX = 32, FI_TY = 32, FI_THREADS = 256;
 #ifndef DATMO_FI_TILE_DEFAULT
-#define DATMO_FI_TILE_DEFAULT 0
+#define DATMO_FI_TILE_DEFAULT 9
 #endif
 
 __device__ __forceinline__ float2 solve_flow(const float g[5]) {
@@ -878,6 +878,268 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter_w(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------
+// F5 + F6 fused, x-marching form (winsize 14 / 15).
+//
+// A CTA owns a band of TY output rows and walks a segment of it left to right in groups of
+// 32 columns.  Per group:
+//   M   M for the 32 NEW columns x (TY + 14) rows (a warp = 32 consecutive pixels of a row, so
+//       the R0 / flow loads are whole aligned lines); only the rows are halo — no column is
+//       ever evaluated twice inside a segment;
+//   V   vertical 15-sums of the new columns (van Herk, thread per (channel, column, half band))
+//       appended to a 46-column window of vertical sums whose first 14 columns are carried
+//       over from the previous groups;
+//   H   horizontal 15-sums over the window -> 32 finished output columns (they trail the new
+//       group by 7), written where M was; the thread then moves its row's last 14 window columns
+//       to the front;
+//   S   2x2 solve, float2 store.
+// M evaluations per output pixel: (TY + 14) / TY x (seg + 16) / seg  (1.30 for TY 64, seg 256)
+// against 1.75 for the 64 x 32 tile kernel above, and the vertical pass never touches a halo
+// column.  Every window sum is still the sum of exactly its own 15 values.
+// ------------------------------------------------------------------------------------
+template <int WIN, int NOUT>
+__device__ __forceinline__ void window_sums(const float* __restrict__ in, const int si, float* __restrict__ out,
+                                            const int so) {
+    constexpr int NIN = NOUT + WIN - 1;
+    float S[WIN];
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) S[j] = in[j * si];
+#pragma unroll
+    for (int j = WIN - 2; j >= 0; --j) S[j] += S[j + 1];
+#pragma unroll
+    for (int base = 0; base < NOUT; base += WIN) {
+        out[base * so] = S[0];
+        float P = 0.f;
+        float nxt[WIN];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) {
+            const int idx = base + WIN + j;
+            if (idx < NIN) {
+                const float v = in[idx * si];
+                nxt[j] = v;
+                P += v;
+            } else {
+                nxt[j] = 0.f;
+            }
+            const int y = base + 1 + j;
+            if (j < WIN - 1 && y < NOUT) out[y * so] = S[j + 1] + P;
+        }
+#pragma unroll
+        for (int j = WIN - 2; j >= 0; --j) nxt[j] += nxt[j + 1];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) S[j] = nxt[j];
+    }
+}
+
+template <int TY_, int NT_, int VSPLIT_, int MINB_, int PIX_>
+struct XmTile {
+    static constexpr int TY = TY_, NT = NT_, VSPLIT = VSPLIT_, MINB = MINB_, PIX = PIX_;
+    static constexpr int HM = 7, WIN = 15;
+    static constexpr int RH = TY + 2 * HM;       // M rows of a group
+    static constexpr int MS = 33;                // row stride of the M / G buffer (32 columns + 1)
+    static constexpr int VW = 46, VS = 47;       // vertical-sum window: 14 carried + 32 new columns; odd stride
+    static constexpr int M_FLOATS = 5 * RH * MS, V_FLOATS = 5 * TY * VS;
+    static constexpr size_t SMEM = static_cast<size_t>(M_FLOATS + V_FLOATS) * sizeof(float);
+    static_assert(TY % VSPLIT == 0, "band must split evenly for the vertical pass");
+};
+
+// base + index as ONE instruction (IMAD.WIDE); left to itself the compiler sign-extends the
+// index and builds the address with a four-instruction carry chain.
+template <int BYTES, typename P>
+__device__ __forceinline__ const P* at_index(const P* base, int i) {
+    unsigned long long r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(i), "n"(BYTES), "l"(base));
+    return reinterpret_cast<const P*>(r);
+}
+
+// Everything one M evaluation gathers.  The R1 taps are loaded unconditionally (index 0 when the
+// displaced position leaves the image) and replaced by selects afterwards: no divergent branch,
+// so the loads of all pixels of a trip are issued back to back.
+struct XmTaps {
+    float4 q, t0, t1, t2, t3;
+    float s, u0, u1, u2, u3;
+    float fx, fy, dx, dy;
+    bool inside;
+};
+
+__device__ __forceinline__ void xm_gather(const float4* r0q, const float* r0s, const float4* r1q, const float* r1s,
+                                          int w, int h, float xf, int gx, int gy, float2 f, XmTaps& T) {
+    const int o = gy * w + gx;
+    T.q = __ldg(at_index<16>(r0q, o));
+    T.s = __ldg(at_index<4>(r0s, o));
+    T.dx = f.x, T.dy = f.y;
+    const float px = xf + f.x, py = static_cast<float>(gy) + f.y;
+    const int ix = __float2int_rd(px), iy = __float2int_rd(py);   // saturating; NaN -> 0
+    T.inside = static_cast<unsigned>(ix) < static_cast<unsigned>(w - 1) &&
+               static_cast<unsigned>(iy) < static_cast<unsigned>(h - 1);
+    T.fx = px - static_cast<float>(ix);
+    T.fy = py - static_cast<float>(iy);
+    const int i00 = T.inside ? iy * w + ix : 0;
+    const float4* pq = at_index<16>(r1q, i00);
+    const float* ps = at_index<4>(r1s, i00);
+    const float4* pq2 = at_index<16>(r1q, i00 + w);
+    const float* ps2 = at_index<4>(r1s, i00 + w);
+    T.t0 = __ldg(pq), T.t1 = __ldg(pq + 1), T.t2 = __ldg(pq2), T.t3 = __ldg(pq2 + 1);
+    T.u0 = __ldg(ps), T.u1 = __ldg(ps + 1), T.u2 = __ldg(ps2), T.u3 = __ldg(ps2 + 1);
+}
+
+// SURVEY.md §3.2 F5 with the out-of-image case folded into selects: r4 = (q2 + q2) / 2 = q2 etc. are exact
+__device__ __forceinline__ void xm_finish(const XmTaps& T, bool border, int w, int h, int gx, int gy, float M[5]) {
+    const float gx1 = 1.f - T.fx, gy1 = 1.f - T.fy;
+    const float a00 = gx1 * gy1, a01 = T.fx * gy1, a10 = gx1 * T.fy, a11 = T.fx * T.fy;
+    float s0 = a00 * T.t0.x + a01 * T.t1.x + a10 * T.t2.x + a11 * T.t3.x;
+    float s1 = a00 * T.t0.y + a01 * T.t1.y + a10 * T.t2.y + a11 * T.t3.y;
+    float s2 = a00 * T.t0.z + a01 * T.t1.z + a10 * T.t2.z + a11 * T.t3.z;
+    float s3 = a00 * T.t0.w + a01 * T.t1.w + a10 * T.t2.w + a11 * T.t3.w;
+    float s4 = a00 * T.u0 + a01 * T.u1 + a10 * T.u2 + a11 * T.u3;
+    if (!T.inside) s0 = 0.f, s1 = 0.f, s2 = T.q.z, s3 = T.q.w, s4 = T.s;
+    float r4 = (T.q.z + s2) * 0.5f;
+    float r5 = (T.q.w + s3) * 0.5f;
+    float r6 = (T.s + s4) * 0.25f;
+    float r2 = (T.q.x - s0) * 0.5f;
+    float r3 = (T.q.y - s1) * 0.5f;
+    r2 += r4 * T.dy + r6 * T.dx;
+    r3 += r6 * T.dy + r5 * T.dx;
+    if (border && (gx < 5 || gx >= w - 5 || gy < 5 || gy >= h - 5)) {
+        const float sc = (gx < 5 ? c_border[gx] : 1.f) * (gx >= w - 5 ? c_border[w - 1 - gx] : 1.f) *
+                         (gy < 5 ? c_border[gy] : 1.f) * (gy >= h - 5 ? c_border[h - 1 - gy] : 1.f);
+        r2 *= sc, r3 *= sc, r4 *= sc, r5 *= sc, r6 *= sc;
+    }
+    M[0] = r4 * r4 + r6 * r6;
+    M[1] = (r4 + r5) * r6;
+    M[2] = r5 * r5 + r6 * r6;
+    M[3] = r4 * r2 + r6 * r3;
+    M[4] = r6 * r2 + r5 * r3;
+}
+
+// M for nc = 1 << ncl2 (32 or 8) columns starting at cx0, rows ry0 .. ry0 + RH - 1, into sM[c][row][col].
+// One instance serves the lead-in, the groups and the tail (ptxas merges separate instances into
+// one 160-register monster); coordinates are clamped unconditionally (replicate border).
+template <typename T>
+__device__ __forceinline__ void xm_m_phase(float* __restrict__ sM, const float4* r0q, const float* r0s,
+                                           const float4* r1q, const float* r1s, const float2* fb, int w, int h,
+                                           int cx0, int ry0, int ncl2) {
+    constexpr int RH = T::RH, MS = T::MS, NW = T::NT / 32;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int col = lane & ((1 << ncl2) - 1), rsub = lane >> ncl2;
+    const int rpw = 32 >> ncl2;  // rows one warp instruction covers
+    const int gx = min(max(cx0 + col, 0), w - 1);
+    const float xf = static_cast<float>(gx);
+    const int step = NW * rpw;
+    // the 5-pixel attenuation band can only be met by groups at the image edge
+    const bool border = cx0 < 5 || cx0 + 32 > w - 5 || ry0 < 5 || ry0 + RH > h - 5;
+    // PIX pixels (rows r, r + step, ..) per trip: all their gathers are issued before any is
+    // consumed, and the next trip's flow vectors are already in flight.  Rows are clamped, so
+    // every load is in bounds even past the last row; only the store is guarded.
+    constexpr int PIX = T::PIX;
+    int r = wi * rpw + rsub;
+    float2 f[PIX];
+#pragma unroll
+    for (int p = 0; p < PIX; ++p) f[p] = __ldg(at_index<8>(fb, min(max(ry0 + r + p * step, 0), h - 1) * w + gx));
+    float* dst = sM + r * MS + col;
+#pragma unroll 1
+    for (; r < RH; r += PIX * step, dst += PIX * step * MS) {
+        XmTaps Ta[PIX];
+        int gy[PIX];
+#pragma unroll
+        for (int p = 0; p < PIX; ++p) {
+            gy[p] = min(max(ry0 + r + p * step, 0), h - 1);
+            xm_gather(r0q, r0s, r1q, r1s, w, h, xf, gx, gy[p], f[p], Ta[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < PIX; ++p) f[p] = __ldg(at_index<8>(fb, min(max(ry0 + r + (PIX + p) * step, 0), h - 1) * w + gx));
+#pragma unroll
+        for (int p = 0; p < PIX; ++p) {
+            float Mv[5];
+            xm_finish(Ta[p], border, w, h, gx, gy[p], Mv);
+            if (p == 0 || r + p * step < RH) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) dst[c * RH * MS + p * step * MS] = Mv[c];
+            }
+        }
+    }
+}
+
+// vertical sums of nc new columns -> window columns vpos0 .. vpos0 + nc - 1
+template <typename T>
+__device__ __forceinline__ void xm_v_phase(const float* sM, float* sV, int vpos0, int ncl2) {
+    constexpr int PART = T::TY / T::VSPLIT;
+    const int ntask = (5 * T::VSPLIT) << ncl2;
+    for (int i = threadIdx.x; i < ntask; i += T::NT) {
+        const int col = i & ((1 << ncl2) - 1), t = i >> ncl2;
+        const int part = t % T::VSPLIT, c = t / T::VSPLIT;
+        window_sums<T::WIN, PART>(sM + (c * T::RH + part * PART) * T::MS + col, T::MS,
+                                  sV + (c * T::TY + part * PART) * T::VS + vpos0 + col, T::VS);
+    }
+}
+
+// horizontal sums over the 46-column window -> 32 output columns in sG[c][row][0..31]; carry the tail
+template <typename T>
+__device__ __forceinline__ void xm_h_phase(float* sV, float* sG) {
+    for (int i = threadIdx.x; i < 5 * T::TY; i += T::NT) {
+        float* v = sV + i * T::VS;  // i = c * TY + row
+        window_sums<T::WIN, 32>(v, 1, sG + i * T::MS, 1);
+#pragma unroll
+        for (int j = 0; j < 14; ++j) v[j] = v[32 + j];
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void xm_solve(const float* __restrict__ sG, float2* __restrict__ fo, int w, int h, int y0,
+                                         int c0, int xlo, int xhi, float norm) {
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int gx = c0 - T::HM + lane;
+    if (gx < xlo || gx >= xhi) return;
+    const int rows = min(T::TY, h - y0);
+    float2* out = fo + static_cast<size_t>(y0 + wi) * w + gx;
+    const float* g = sG + wi * T::MS + lane;
+    for (int row = wi; row < rows; row += T::NT / 32, out += (T::NT / 32) * w, g += (T::NT / 32) * T::MS) {
+        float v[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) v[c] = g[c * T::TY * T::MS] * norm;
+        *out = solve_flow(v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(T::NT, T::MINB) k_flow_iter_xm(const float* __restrict__ R0,
+                                                                 const float* __restrict__ R1,
+                                                                 const float2* __restrict__ flow_in,
+                                                                 float2* __restrict__ flow_out, int w, int h, int seg,
+                                                                 float norm) {
+    extern __shared__ float sM[];     // [5][RH][MS]; reused as G [5][TY][MS] between the H and S phases
+    float* sV = sM + T::M_FLOATS;     // [5][TY][VS]
+    const int x0 = blockIdx.x * seg, y0 = blockIdx.y * T::TY, b = blockIdx.z;
+    const int xhi = min(x0 + seg, w);
+    const int ngroups = (xhi - x0 + 31) >> 5;
+    const int ry0 = y0 - T::HM;
+    const size_t plane = static_cast<size_t>(w) * h;
+    const RView R0b = r_view(R0, gridDim.z, b, plane), R1b = r_view(R1, gridDim.z, b, plane);
+    const float4* r0q = R0b.q;
+    const float* r0s = R0b.s;
+    const float4* r1q = R1b.q;
+    const float* r1s = R1b.s;
+    const float2* fb = flow_in + static_cast<size_t>(b) * plane;
+    float2* fo = flow_out + static_cast<size_t>(b) * plane;
+    // k = -1: lead-in, the 8 columns left of the segment (only the last 7 are read) -> window columns
+    // 6..13; k = ngroups: tail, the 8 columns right of it that finish its last 7 outputs
+    for (int k = -1; k <= ngroups; ++k) {
+        const bool lead = k < 0, tail = k == ngroups;
+        const int c0 = lead ? x0 - 8 : x0 + 32 * k;
+        if (tail && c0 - T::HM >= xhi) break;
+        const int ncl2 = (lead || tail) ? 3 : 5;
+        __syncthreads();  // the previous V (reads sM) / S (reads G) phase is done
+        xm_m_phase<T>(sM, r0q, r0s, r1q, r1s, fb, w, h, c0, ry0, ncl2);
+        __syncthreads();
+        xm_v_phase<T>(sM, sV, lead ? 6 : 14, ncl2);
+        if (lead) continue;
+        __syncthreads();
+        xm_h_phase<T>(sV, sM);
+        __syncthreads();
+        xm_solve<T>(sM, fo, w, h, y0, c0, x0, xhi, norm);
+    }
+}
+
 size_t flow_iter_smem(int m) {
     int RW = FI_TX + 2 * m, RH = FI_TY + 2 * m, SW = RW | 1;
     return static_cast<size_t>(5) * (RH + FI_TY) * SW * sizeof(float);
@@ -976,6 +1238,43 @@ int launch_flow_iter_w(datmo_ctx* h, const float* R0, const float* R1, const flo
     return DATMO_OK;
 }
 
+// Segment length for the x-marching kernel: the multiple of 32 columns that minimises
+// (CTA waves, rounded up) x (columns evaluated per segment, lead-in and tail included).
+int xm_pick_segment(int w, int bands, int B, int slots) {
+    int best = 32;
+    double best_cost = 1e300;
+    for (int seg = 64; seg <= ((w + 31) & ~31); seg += 32) {
+        const int nseg = ceil_div(w, seg);
+        const double ctas = static_cast<double>(nseg) * bands * B;
+        const double waves = ceil(ctas / slots);
+        const double cost = waves * (seg + 16 + 24);  // + ~24 columns' worth of per-CTA fixed cost
+        if (cost < best_cost - 1e-9) best_cost = cost, best = seg;
+    }
+    return best;
+}
+
+template <typename T>
+int launch_flow_iter_xm(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, float* flow_out, int w,
+                        int hh, int B, float norm) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter_xm<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(T::SMEM)));
+        attr_set = true;
+    }
+    const int bands = ceil_div(hh, T::TY);
+    static const int seg_env = getenv("DATMO_XM_SEG") ? atoi(getenv("DATMO_XM_SEG")) : 0;
+    const int seg = seg_env > 0 ? ((seg_env + 31) & ~31) : xm_pick_segment(w, bands, B, h->sm_count * T::MINB);
+    dim3 g(ceil_div(w, seg), bands, B);
+    {
+        LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
+        k_flow_iter_xm<T><<<g, T::NT, T::SMEM, h->stream>>>(R0, R1, reinterpret_cast<const float2*>(flow_in),
+                                                           reinterpret_cast<float2*>(flow_out), w, hh, seg, norm);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
 template <bool FUSED>
 int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, const float* Min,
                      float* flow_out, int w, int hh, int B, int winsize) {
@@ -986,6 +1285,19 @@ int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float
         // alternatives measured in DESIGN.md §5 (1: 32x32 tile, one pixel per trip, 4 CTAs/SM;
         // 2: 64x64 tile, 512 threads, 1 CTA/SM); all three land within 3 % of each other
         static const int tile = flow_tile_choice();
+        if (FUSED) {
+            switch (tile) {
+                case 3: return launch_flow_iter_xm<XmTile<64, 320, 2, 2, 1>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                case 4: return launch_flow_iter_xm<XmTile<48, 320, 2, 2, 1>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                case 5: return launch_flow_iter_xm<XmTile<32, 160, 1, 3, 1>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                case 6: return launch_flow_iter_xm<XmTile<64, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                case 7: return launch_flow_iter_xm<XmTile<32, 160, 1, 3, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                case 8: return launch_flow_iter_xm<XmTile<48, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                case 9: return launch_flow_iter_xm<XmTile<46, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                case 10: return launch_flow_iter_xm<XmTile<26, 320, 1, 3, 1>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                default: break;
+            }
+        }
         switch (tile) {
             case 1: return launch_flow_iter_w<32, 32, 256, 4, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
             case 2: return launch_flow_iter_w<64, 64, 512, 1, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
