@@ -900,40 +900,83 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter_w(const float* __restric
 template <int WIN, int NOUT>
 __device__ __forceinline__ void window_sums(const float* __restrict__ in, const int si, float* __restrict__ out,
                                             const int so) {
+    // inputs are read one block of WIN ahead of their use, WIN independent loads at a time, so the
+    // add chains never wait on shared-memory latency
     constexpr int NIN = NOUT + WIN - 1;
-    float S[WIN];
+    float S[WIN], nxt[WIN];
 #pragma unroll
     for (int j = 0; j < WIN; ++j) S[j] = in[j * si];
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) nxt[j] = WIN + j < NIN ? in[(WIN + j) * si] : 0.f;
 #pragma unroll
     for (int j = WIN - 2; j >= 0; --j) S[j] += S[j + 1];
 #pragma unroll
     for (int base = 0; base < NOUT; base += WIN) {
-        out[base * so] = S[0];
-        float P = 0.f;
-        float nxt[WIN];
+        float ahead[WIN];
 #pragma unroll
         for (int j = 0; j < WIN; ++j) {
-            const int idx = base + WIN + j;
-            if (idx < NIN) {
-                const float v = in[idx * si];
-                nxt[j] = v;
-                P += v;
-            } else {
-                nxt[j] = 0.f;
-            }
+            const int idx = base + 2 * WIN + j;
+            ahead[j] = (base + WIN < NOUT && idx < NIN) ? in[idx * si] : 0.f;
+        }
+        out[base * so] = S[0];
+        float P = 0.f;
+#pragma unroll
+        for (int j = 0; j < WIN - 1; ++j) {
+            P += nxt[j];
             const int y = base + 1 + j;
-            if (j < WIN - 1 && y < NOUT) out[y * so] = S[j + 1] + P;
+            if (y < NOUT) out[y * so] = S[j + 1] + P;
         }
 #pragma unroll
         for (int j = WIN - 2; j >= 0; --j) nxt[j] += nxt[j + 1];
 #pragma unroll
-        for (int j = 0; j < WIN; ++j) S[j] = nxt[j];
+        for (int j = 0; j < WIN; ++j) S[j] = nxt[j], nxt[j] = ahead[j];
     }
 }
 
-template <int TY_, int NT_, int VSPLIT_, int MINB_, int PIX_>
+// In-place form for the horizontal pass over a row v[0 .. NOUT + WIN - 2] (stride 1): output j
+// lands on v[WIN - 1 + j] and the last WIN - 1 inputs move to the front, i.e. the row is ready to
+// receive the next NOUT new values behind them.  Safe because a block's outputs are stored only
+// after the inputs two blocks ahead are in registers, and everything is program-ordered.
+template <int WIN, int NOUT>
+__device__ __forceinline__ void window_sums_carry(float* v) {
+    constexpr int NIN = NOUT + WIN - 1;
+    float S[WIN], nxt[WIN], carry[WIN - 1];
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) S[j] = v[j];
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) nxt[j] = WIN + j < NIN ? v[WIN + j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < WIN - 1; ++j) carry[j] = v[NOUT + j];
+#pragma unroll
+    for (int j = WIN - 2; j >= 0; --j) S[j] += S[j + 1];
+#pragma unroll
+    for (int base = 0; base < NOUT; base += WIN) {
+        float ahead[WIN];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) {
+            const int idx = base + 2 * WIN + j;
+            ahead[j] = (base + WIN < NOUT && idx < NIN) ? v[idx] : 0.f;
+        }
+        v[WIN - 1 + base] = S[0];
+        float P = 0.f;
+#pragma unroll
+        for (int j = 0; j < WIN - 1; ++j) {
+            P += nxt[j];
+            const int y = base + 1 + j;
+            if (y < NOUT) v[WIN - 1 + y] = S[j + 1] + P;
+        }
+#pragma unroll
+        for (int j = WIN - 2; j >= 0; --j) nxt[j] += nxt[j + 1];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) S[j] = nxt[j], nxt[j] = ahead[j];
+    }
+#pragma unroll
+    for (int j = 0; j < WIN - 1; ++j) v[j] = carry[j];
+}
+
+template <int TY_, int NT_, int VSPLIT_, int MINB_, int PIX_, int OPT_ = 0>
 struct XmTile {
-    static constexpr int TY = TY_, NT = NT_, VSPLIT = VSPLIT_, MINB = MINB_, PIX = PIX_;
+    static constexpr int TY = TY_, NT = NT_, VSPLIT = VSPLIT_, MINB = MINB_, PIX = PIX_, OPT = OPT_;
     static constexpr int HM = 7, WIN = 15;
     static constexpr int RH = TY + 2 * HM;       // M rows of a group
     static constexpr int MS = 33;                // row stride of the M / G buffer (32 columns + 1)
@@ -1012,6 +1055,32 @@ __device__ __forceinline__ void xm_finish(const XmTaps& T, bool border, int w, i
     M[4] = r6 * r2 + r5 * r3;
 }
 
+// L2 prefetch of everything the NEXT group's M phase will read (R0, R1 at zero displacement, flow):
+// a group's columns are new to the whole GPU, so without this every gather of the M phase waits on
+// DRAM; with it they wait on L2.  One 128-byte line per instruction, 12 lines per row.
+template <typename T>
+__device__ __forceinline__ void xm_prefetch(const float4* r0q, const float* r0s, const float4* r1q,
+                                            const float* r1s, const float2* fb, int w, int h, int cx, int ry0) {
+    if (cx >= w) return;
+    for (int i = threadIdx.x; i < T::RH * 12; i += T::NT) {
+        const int row = i / 12, j = i - row * 12;
+        const int gy = min(max(ry0 + row, 0), h - 1);
+        const int o = gy * w + cx;
+        const char* p;
+        if (j < 4)
+            p = reinterpret_cast<const char*>(r0q + o) + j * 128;
+        else if (j < 8)
+            p = reinterpret_cast<const char*>(r1q + o) + (j - 4) * 128;
+        else if (j == 8)
+            p = reinterpret_cast<const char*>(r0s + o);
+        else if (j == 9)
+            p = reinterpret_cast<const char*>(r1s + o);
+        else
+            p = reinterpret_cast<const char*>(fb + o) + (j - 10) * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+}
+
 // M for nc = 1 << ncl2 (32 or 8) columns starting at cx0, rows ry0 .. ry0 + RH - 1, into sM[c][row][col].
 // One instance serves the lead-in, the groups and the tail (ptxas merges separate instances into
 // one 160-register monster); coordinates are clamped unconditionally (replicate border).
@@ -1032,29 +1101,64 @@ __device__ __forceinline__ void xm_m_phase(float* __restrict__ sM, const float4*
     // consumed, and the next trip's flow vectors are already in flight.  Rows are clamped, so
     // every load is in bounds even past the last row; only the store is guarded.
     constexpr int PIX = T::PIX;
-    int r = wi * rpw + rsub;
-    float2 f[PIX];
+    const int r0 = wi * rpw + rsub;
+    float* dst = sM + r0 * MS + col;
+    if constexpr ((T::OPT & 2) != 0) {
+        // every trip's flow vectors loaded up front, trips unrolled
+        constexpr int TRIPS = (RH + PIX * NW - 1) / (PIX * NW);  // 32-column groups; the 8-column ones need one
+        float2 f[TRIPS][PIX];
 #pragma unroll
-    for (int p = 0; p < PIX; ++p) f[p] = __ldg(at_index<8>(fb, min(max(ry0 + r + p * step, 0), h - 1) * w + gx));
-    float* dst = sM + r * MS + col;
-#pragma unroll 1
-    for (; r < RH; r += PIX * step, dst += PIX * step * MS) {
-        XmTaps Ta[PIX];
-        int gy[PIX];
+        for (int t = 0; t < TRIPS; ++t)
 #pragma unroll
-        for (int p = 0; p < PIX; ++p) {
-            gy[p] = min(max(ry0 + r + p * step, 0), h - 1);
-            xm_gather(r0q, r0s, r1q, r1s, w, h, xf, gx, gy[p], f[p], Ta[p]);
+            for (int p = 0; p < PIX; ++p)
+                f[t][p] = __ldg(at_index<8>(fb, min(max(ry0 + r0 + (t * PIX + p) * step, 0), h - 1) * w + gx));
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            const int r = r0 + t * PIX * step;
+            if (r >= RH) break;
+            XmTaps Ta[PIX];
+            int gy[PIX];
+#pragma unroll
+            for (int p = 0; p < PIX; ++p) {
+                gy[p] = min(max(ry0 + r + p * step, 0), h - 1);
+                xm_gather(r0q, r0s, r1q, r1s, w, h, xf, gx, gy[p], f[t][p], Ta[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < PIX; ++p) {
+                float Mv[5];
+                xm_finish(Ta[p], border, w, h, gx, gy[p], Mv);
+                if (p == 0 || r + p * step < RH) {
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) dst[c * RH * MS + (t * PIX + p) * step * MS] = Mv[c];
+                }
+            }
         }
+    } else {
+        int r = r0;
+        float2 f[PIX];
 #pragma unroll
-        for (int p = 0; p < PIX; ++p) f[p] = __ldg(at_index<8>(fb, min(max(ry0 + r + (PIX + p) * step, 0), h - 1) * w + gx));
+        for (int p = 0; p < PIX; ++p)
+            f[p] = __ldg(at_index<8>(fb, min(max(ry0 + r + p * step, 0), h - 1) * w + gx));
+#pragma unroll 1
+        for (; r < RH; r += PIX * step, dst += PIX * step * MS) {
+            XmTaps Ta[PIX];
+            int gy[PIX];
 #pragma unroll
-        for (int p = 0; p < PIX; ++p) {
-            float Mv[5];
-            xm_finish(Ta[p], border, w, h, gx, gy[p], Mv);
-            if (p == 0 || r + p * step < RH) {
+            for (int p = 0; p < PIX; ++p) {
+                gy[p] = min(max(ry0 + r + p * step, 0), h - 1);
+                xm_gather(r0q, r0s, r1q, r1s, w, h, xf, gx, gy[p], f[p], Ta[p]);
+            }
 #pragma unroll
-                for (int c = 0; c < 5; ++c) dst[c * RH * MS + p * step * MS] = Mv[c];
+            for (int p = 0; p < PIX; ++p)
+                f[p] = __ldg(at_index<8>(fb, min(max(ry0 + r + (PIX + p) * step, 0), h - 1) * w + gx));
+#pragma unroll
+            for (int p = 0; p < PIX; ++p) {
+                float Mv[5];
+                xm_finish(Ta[p], border, w, h, gx, gy[p], Mv);
+                if (p == 0 || r + p * step < RH) {
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) dst[c * RH * MS + p * step * MS] = Mv[c];
+                }
             }
         }
     }
@@ -1073,30 +1177,27 @@ __device__ __forceinline__ void xm_v_phase(const float* sM, float* sV, int vpos0
     }
 }
 
-// horizontal sums over the 46-column window -> 32 output columns in sG[c][row][0..31]; carry the tail
+// horizontal sums over the 46-column window, in place: the 32 finished columns land on window
+// columns 14..45 (where the next group's vertical sums will be written after the solve has read
+// them) and the last 14 window columns move to the front
 template <typename T>
-__device__ __forceinline__ void xm_h_phase(float* sV, float* sG) {
-    for (int i = threadIdx.x; i < 5 * T::TY; i += T::NT) {
-        float* v = sV + i * T::VS;  // i = c * TY + row
-        window_sums<T::WIN, 32>(v, 1, sG + i * T::MS, 1);
-#pragma unroll
-        for (int j = 0; j < 14; ++j) v[j] = v[32 + j];
-    }
+__device__ __forceinline__ void xm_h_phase(float* sV) {
+    for (int i = threadIdx.x; i < 5 * T::TY; i += T::NT) window_sums_carry<T::WIN, 32>(sV + i * T::VS);  // i = c * TY + row
 }
 
 template <typename T>
-__device__ __forceinline__ void xm_solve(const float* __restrict__ sG, float2* __restrict__ fo, int w, int h, int y0,
-                                         int c0, int xlo, int xhi, float norm) {
+__device__ __forceinline__ void xm_solve(const float* sV, float2* __restrict__ fo, int w, int h, int y0, int c0,
+                                         int xlo, int xhi, float norm) {
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int gx = c0 - T::HM + lane;
     if (gx < xlo || gx >= xhi) return;
     const int rows = min(T::TY, h - y0);
     float2* out = fo + static_cast<size_t>(y0 + wi) * w + gx;
-    const float* g = sG + wi * T::MS + lane;
-    for (int row = wi; row < rows; row += T::NT / 32, out += (T::NT / 32) * w, g += (T::NT / 32) * T::MS) {
+    const float* g = sV + wi * T::VS + (T::WIN - 1) + lane;
+    for (int row = wi; row < rows; row += T::NT / 32, out += (T::NT / 32) * w, g += (T::NT / 32) * T::VS) {
         float v[5];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) v[c] = g[c * T::TY * T::MS] * norm;
+        for (int c = 0; c < 5; ++c) v[c] = g[c * T::TY * T::VS] * norm;
         *out = solve_flow(v);
     }
 }
@@ -1106,8 +1207,8 @@ __global__ void __launch_bounds__(T::NT, T::MINB) k_flow_iter_xm(const float* __
                                                                  const float* __restrict__ R1,
                                                                  const float2* __restrict__ flow_in,
                                                                  float2* __restrict__ flow_out, int w, int h, int seg,
-                                                                 float norm) {
-    extern __shared__ float sM[];     // [5][RH][MS]; reused as G [5][TY][MS] between the H and S phases
+                                                                 float norm, int prefetch) {
+    extern __shared__ float sM[];     // [5][RH][MS]
     float* sV = sM + T::M_FLOATS;     // [5][TY][VS]
     const int x0 = blockIdx.x * seg, y0 = blockIdx.y * T::TY, b = blockIdx.z;
     const int xhi = min(x0 + seg, w);
@@ -1128,15 +1229,17 @@ __global__ void __launch_bounds__(T::NT, T::MINB) k_flow_iter_xm(const float* __
         const int c0 = lead ? x0 - 8 : x0 + 32 * k;
         if (tail && c0 - T::HM >= xhi) break;
         const int ncl2 = (lead || tail) ? 3 : 5;
-        __syncthreads();  // the previous V (reads sM) / S (reads G) phase is done
+        // M(k) may start as soon as V(k-1) has left sM: the barrier in front of H(k-1) saw to that,
+        // so the solve of group k-1 and this M phase share one barrier interval
+        if (prefetch && k + 1 < ngroups) xm_prefetch<T>(r0q, r0s, r1q, r1s, fb, w, h, x0 + 32 * (k + 1), ry0);
         xm_m_phase<T>(sM, r0q, r0s, r1q, r1s, fb, w, h, c0, ry0, ncl2);
-        __syncthreads();
+        __syncthreads();  // M complete; S(k-1) has read the window columns V(k) overwrites
         xm_v_phase<T>(sM, sV, lead ? 6 : 14, ncl2);
+        __syncthreads();
         if (lead) continue;
+        xm_h_phase<T>(sV);
         __syncthreads();
-        xm_h_phase<T>(sV, sM);
-        __syncthreads();
-        xm_solve<T>(sM, fo, w, h, y0, c0, x0, xhi, norm);
+        xm_solve<T>(sV, fo, w, h, y0, c0, x0, xhi, norm);
     }
 }
 
@@ -1265,11 +1368,13 @@ int launch_flow_iter_xm(datmo_ctx* h, const float* R0, const float* R1, const fl
     const int bands = ceil_div(hh, T::TY);
     static const int seg_env = getenv("DATMO_XM_SEG") ? atoi(getenv("DATMO_XM_SEG")) : 0;
     const int seg = seg_env > 0 ? ((seg_env + 31) & ~31) : xm_pick_segment(w, bands, B, h->sm_count * T::MINB);
+    static const int prefetch = getenv("DATMO_XM_PREFETCH") ? atoi(getenv("DATMO_XM_PREFETCH")) : 1;
     dim3 g(ceil_div(w, seg), bands, B);
     {
         LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
         k_flow_iter_xm<T><<<g, T::NT, T::SMEM, h->stream>>>(R0, R1, reinterpret_cast<const float2*>(flow_in),
-                                                           reinterpret_cast<float2*>(flow_out), w, hh, seg, norm);
+                                                           reinterpret_cast<float2*>(flow_out), w, hh, seg, norm,
+                                                           prefetch);
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
@@ -1293,8 +1398,9 @@ int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float
                 case 6: return launch_flow_iter_xm<XmTile<64, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
                 case 7: return launch_flow_iter_xm<XmTile<32, 160, 1, 3, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
                 case 8: return launch_flow_iter_xm<XmTile<48, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                case 9: return launch_flow_iter_xm<XmTile<46, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                case 9: return launch_flow_iter_xm<XmTile<46, 320, 2, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
                 case 10: return launch_flow_iter_xm<XmTile<26, 320, 1, 3, 1>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+                case 12: return launch_flow_iter_xm<XmTile<46, 320, 2, 2, 2, 0>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
                 default: break;
             }
         }

@@ -19,12 +19,20 @@ for r in rows[hi[0] + 1:end]:
         ln = int(r[0])
     except ValueError:
         continue
+    try:  # source lines with embedded quotes (inline asm) come out of ncu's CSV mis-split
+        n_inst = float(r[idx["Instructions Executed"]].replace("-", "0") or 0)
+        n_samp = float(r[idx["# Samples"]].replace("-", "0") or 0)
+    except ValueError:
+        continue
     d = per.setdefault(ln, [r[1], 0, 0, collections.Counter()])
-    d[1] += float(r[idx["Instructions Executed"]] or 0)
-    d[2] += float(r[idx["# Samples"]] or 0)
+    d[1] += n_inst
+    d[2] += n_samp
     for k in h:
         if k.startswith("stall_") and "Not" not in k and r[idx[k]]:
-            d[3][k] += float(r[idx[k]])
+            try:
+                d[3][k] += float(r[idx[k]])
+            except ValueError:
+                pass
 ti = sum(d[1] for d in per.values())
 ts = sum(d[2] for d in per.values())
 print("warp instructions", ti, "samples", ts)
