@@ -86,6 +86,52 @@ std::vector<float> gaussian_kernel(int ksize, double sigma) {
     return k;
 }
 
+// INTER_LINEAR source tap of destination index d (F2), host side: src = (d+0.5)*S/D - 0.5 in fp64,
+// then the two clamp rules.
+inline void resize_tap_host(int d, int S, double ratio, int& s, double& f) {
+    const double src = (d + 0.5) * ratio - 0.5;
+    const double fl = floor(src);
+    s = static_cast<int>(fl);
+    f = src - fl;
+    if (s < 0) s = 0, f = 0;
+    if (s >= S - 1) s = S - 1, f = 0;
+}
+
+// Tables of one pyramid layer, appended to `out` as 32-bit words (the block starts 8-byte aligned):
+//   hf [w] double | vf [h] double | hx0 [w] int | vy0 [h] int | g [ksize] float (+ pad to even)
+// hx0 = first source column of an output column's blur window (tap - ksize / 2), hf its blend
+// weight towards the next tap; likewise for rows.
+size_t pyr_table_words(const FbLayer& L) {
+    return 3 * static_cast<size_t>(L.w + L.h) + ((L.ksize + 1) & ~1) + ((L.w + L.h) & 1);
+}
+
+void pyr_tables(int H, int W, const FbLayer& L, std::vector<float>& out) {
+    const int r = L.ksize >> 1;
+    const std::vector<float> g = gaussian_kernel(L.ksize, L.sigma);
+    const size_t base = out.size();  // even by construction
+    out.resize(base + pyr_table_words(L), 0.f);
+    char* p = reinterpret_cast<char*>(out.data() + base);
+    char* hf = p;
+    char* vf = hf + sizeof(double) * L.w;
+    char* hx = vf + sizeof(double) * L.h;
+    char* vy = hx + sizeof(int32_t) * L.w;
+    char* gk = vy + sizeof(int32_t) * L.h;
+    auto fill = [&](int n_out, int n_src, char* first, char* frac) {
+        const double ratio = static_cast<double>(n_src) / n_out;
+        for (int d = 0; d < n_out; ++d) {
+            int sidx;
+            double f;
+            resize_tap_host(d, n_src, ratio, sidx, f);
+            const int32_t x0 = sidx - r;
+            memcpy(first + sizeof(int32_t) * d, &x0, sizeof(int32_t));
+            memcpy(frac + sizeof(double) * d, &f, sizeof(double));
+        }
+    };
+    fill(L.w, W, hx, hf);
+    fill(L.h, H, vy, vf);
+    memcpy(gk, g.data(), sizeof(float) * L.ksize);
+}
+
 constexpr int POLY_MAX_N = 16;
 struct PolyCoef {
     float g[POLY_MAX_N + 1], xg[POLY_MAX_N + 1], xxg[POLY_MAX_N + 1];
@@ -215,56 +261,119 @@ __device__ __forceinline__ void r_out(float* R, int B, int bz, size_t n, float4*
 // F2: pyramid image.  Horizontal Gaussian + horizontal resize, then vertical Gaussian
 // + vertical resize; the blur is only evaluated at the taps the resize reads.
 // ------------------------------------------------------------------------------------
+// The source tap and the fp64 blend weight of every output column (row) do not depend on the row
+// (column): the host tabulates them once per layer (pyr_tables).
+// Horizontal pass: a CTA stages PYR_ROWS source rows in shared memory as f32 (BORDER_REFLECT_101
+// applied while staging, 16 pixels per load) and every thread produces one output column for all
+// of them.  Arithmetic (order of the f32 tap sums, fp64 blend) is that of cv2's blur-then-resize.
+constexpr int PYR_ROWS = 4;
+
+// four pixels -> one 16-byte shared store (consecutive lanes, consecutive chunks: conflict-free)
+__device__ __forceinline__ float4 load4_px(const uint8_t* p) {
+    const unsigned v = *reinterpret_cast<const unsigned*>(p);
+    return make_float4(static_cast<float>(v & 0xffu), static_cast<float>((v >> 8) & 0xffu),
+                       static_cast<float>((v >> 16) & 0xffu), static_cast<float>(v >> 24));
+}
+__device__ __forceinline__ float4 load4_px(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
 template <typename SrcT>
-__global__ void __launch_bounds__(128) k_pyr_h(const SrcT* __restrict__ src, float* __restrict__ T, int H, int W,
-                                               int w, const float* __restrict__ kern, int ksize, double ratio) {
-    int dx = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    int b = blockIdx.z;
-    if (dx >= w) return;
-    int sx;
-    double fx;
-    resize_tap(dx, W, ratio, sx, fx);
-    const SrcT* row = src + (static_cast<size_t>(b) * H + y) * W;
-    int r = ksize >> 1;
-    float a0 = 0.f, a1 = 0.f;
-    if (sx - r >= 0 && sx + 1 + r < W) {
-        const SrcT* p = row + sx - r;
-        for (int i = 0; i < ksize; ++i) {
-            float kv = kern[i];
-            a0 = fmaf(kv, load_px(p + i), a0);
-            a1 = fmaf(kv, load_px(p + i + 1), a1);
+__global__ void __launch_bounds__(256) k_pyr_h(const SrcT* __restrict__ src, float* __restrict__ T, int H, int W,
+                                               int w, const float* __restrict__ kern, int ksize,
+                                               const int* __restrict__ x0tab, const double* __restrict__ ftab,
+                                               int vec) {
+    extern __shared__ __align__(16) float srow[];  // [PYR_ROWS][SW]; element LM + c of a row is source column c
+    const int r = ksize >> 1, LM = (r + 3) & ~3, SW = LM + ((W + r + 1 + 3) & ~3);
+    const int y0 = blockIdx.x * PYR_ROWS, b = blockIdx.y;
+    if (vec) {
+        // interior, four pixels per thread and trip (W % 4 == 0 and a suitably aligned image)
+        const int per_row = W >> 2;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < PYR_ROWS * per_row; i += 256) {
+            const int rr = i / per_row, j = i - rr * per_row;
+            const int y = min(y0 + rr, H - 1);
+            *reinterpret_cast<float4*>(srow + rr * SW + LM + 4 * j) =
+                load4_px(src + (static_cast<size_t>(b) * H + y) * W + 4 * j);
+        }
+        // the reflected margins: r columns on the left, r + 1 on the right
+        const int nm = 2 * r + 1;
+        for (int i = threadIdx.x; i < PYR_ROWS * nm; i += 256) {
+            const int rr = i / nm, m = i - rr * nm;
+            const int c = m < r ? m - r : W + (m - r);
+            const int y = min(y0 + rr, H - 1);
+            srow[rr * SW + LM + c] = load_px(src + (static_cast<size_t>(b) * H + y) * W + reflect101(c, W));
         }
     } else {
-        for (int i = 0; i < ksize; ++i) {
-            float kv = kern[i];
-            a0 = fmaf(kv, load_px(row + reflect101(sx + i - r, W)), a0);
-            a1 = fmaf(kv, load_px(row + reflect101(sx + 1 + i - r, W)), a1);
+        const int span = W + 2 * r + 1;
+        for (int i = threadIdx.x; i < PYR_ROWS * span; i += 256) {
+            const int rr = i / span, c = i - rr * span - r;
+            const int y = min(y0 + rr, H - 1);
+            srow[rr * SW + LM + c] = load_px(src + (static_cast<size_t>(b) * H + y) * W + reflect101(c, W));
         }
     }
-    float v = fx == 0.0 ? a0 : static_cast<float>((1.0 - fx) * a0 + fx * a1);
-    T[(static_cast<size_t>(b) * H + y) * w + dx] = v;
+    __syncthreads();
+    for (int xo = threadIdx.x; xo < w; xo += 256) {
+        const float* s0 = srow + x0tab[xo] + LM;
+        const double fx = ftab[xo];
+        float a0[PYR_ROWS], a1[PYR_ROWS];
+#pragma unroll
+        for (int rr = 0; rr < PYR_ROWS; ++rr) a0[rr] = 0.f, a1[rr] = 0.f;
+        for (int i = 0; i < ksize; ++i) {
+            const float kv = kern[i];
+#pragma unroll
+            for (int rr = 0; rr < PYR_ROWS; ++rr) {
+                a0[rr] = fmaf(kv, s0[rr * SW + i], a0[rr]);
+                a1[rr] = fmaf(kv, s0[rr * SW + i + 1], a1[rr]);
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < PYR_ROWS; ++rr)
+            if (y0 + rr < H)
+                T[(static_cast<size_t>(b) * H + y0 + rr) * w + xo] =
+                    fx == 0.0 ? a0[rr] : static_cast<float>((1.0 - fx) * a0[rr] + fx * a1[rr]);
+    }
 }
 
+// Vertical pass: a thread owns an output column and PYR_ROWS consecutive output rows whose tap
+// chains are independent, so their loads overlap.
 __global__ void __launch_bounds__(128) k_pyr_v(const float* __restrict__ T, float* __restrict__ out, int H, int w,
-                                               int h, const float* __restrict__ kern, int ksize, double ratio) {
-    int dx = blockIdx.x * blockDim.x + threadIdx.x;
-    int dy = blockIdx.y;
-    int b = blockIdx.z;
-    if (dx >= w) return;
-    int sy;
-    double fy;
-    resize_tap(dy, H, ratio, sy, fy);
-    const float* base = T + static_cast<size_t>(b) * H * w + dx;
-    int r = ksize >> 1;
-    float a0 = 0.f, a1 = 0.f;
-    for (int i = 0; i < ksize; ++i) {
-        float kv = kern[i];
-        a0 = fmaf(kv, base[static_cast<size_t>(reflect101(sy + i - r, H)) * w], a0);
-        a1 = fmaf(kv, base[static_cast<size_t>(reflect101(sy + 1 + i - r, H)) * w], a1);
+                                               int h, const float* __restrict__ kern, int ksize,
+                                               const int* __restrict__ y0tab, const double* __restrict__ ftab) {
+    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yo0 = blockIdx.y * PYR_ROWS, b = blockIdx.z;
+    if (xo >= w) return;
+    const float* base = T + static_cast<size_t>(b) * H * w + xo;
+    int ys[PYR_ROWS];
+    float a0[PYR_ROWS], a1[PYR_ROWS];
+#pragma unroll
+    for (int rr = 0; rr < PYR_ROWS; ++rr) {
+        ys[rr] = y0tab[min(yo0 + rr, h - 1)];
+        a0[rr] = 0.f, a1[rr] = 0.f;
     }
-    float v = fy == 0.0 ? a0 : static_cast<float>((1.0 - fy) * a0 + fy * a1);
-    out[(static_cast<size_t>(b) * h + dy) * w + dx] = v;
+    for (int i = 0; i <= ksize; ++i) {
+        // source row ys + i feeds tap i of a0 and tap i - 1 of a1: one load for both
+        const float k0 = i < ksize ? kern[i] : 0.f, k1 = i > 0 ? kern[i - 1] : 0.f;
+        float v[PYR_ROWS];
+#pragma unroll
+        for (int rr = 0; rr < PYR_ROWS; ++rr) {
+            int y = ys[rr] + i;
+            if (static_cast<unsigned>(y) >= static_cast<unsigned>(H)) y = reflect101(y, H);
+            v[rr] = base[static_cast<size_t>(y) * w];
+        }
+#pragma unroll
+        for (int rr = 0; rr < PYR_ROWS; ++rr) {
+            if (i < ksize) a0[rr] = fmaf(k0, v[rr], a0[rr]);
+            if (i > 0) a1[rr] = fmaf(k1, v[rr], a1[rr]);
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < PYR_ROWS; ++rr) {
+        const int yo = yo0 + rr;
+        if (yo < h) {
+            const double fy = ftab[yo];
+            out[(static_cast<size_t>(b) * h + yo) * w + xo] =
+                fy == 0.0 ? a0[rr] : static_cast<float>((1.0 - fy) * a0[rr] + fy * a1[rr]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -1251,23 +1360,45 @@ size_t flow_iter_smem(int m) {
 // ------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------
-int launch_pyr(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, const FbLayer& L, const float* d_kern,
+int launch_pyr(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, const FbLayer& L, const float* d_tab,
                float* T, float* out) {
-    dim3 g1(ceil_div(L.w, 128), H, B);
+    const double* hf = reinterpret_cast<const double*>(d_tab);
+    const double* vf = hf + L.w;
+    const int* hx = reinterpret_cast<const int*>(vf + L.h);
+    const int* vy = hx + L.w;
+    const float* gk = reinterpret_cast<const float*>(vy + L.h);
+    const int pr = L.ksize >> 1;
+    const size_t smem = static_cast<size_t>(PYR_ROWS) * (((pr + 3) & ~3) + ((W + pr + 1 + 3) & ~3)) * sizeof(float);
+    DATMO_REQUIRE(h, smem <= 227 * 1024, "image too wide for the pyramid row staging");
+    static size_t configured_u8 = 48 * 1024, configured_f32 = 48 * 1024;
+    dim3 g1(ceil_div(H, PYR_ROWS), B);
+    const int vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0;
     {
-        LaunchScope ls(h, DATMO_TAG_PYRAMID);
-        if (dtype == DATMO_U8)
-            k_pyr_h<uint8_t><<<g1, 128, 0, h->stream>>>(static_cast<const uint8_t*>(img), T, H, W, L.w, d_kern,
-                                                        L.ksize, static_cast<double>(W) / L.w);
-        else
-            k_pyr_h<float><<<g1, 128, 0, h->stream>>>(static_cast<const float*>(img), T, H, W, L.w, d_kern, L.ksize,
-                                                      static_cast<double>(W) / L.w);
+        if (dtype == DATMO_U8) {
+            if (smem > configured_u8) {
+                DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_pyr_h<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         static_cast<int>(smem)));
+                configured_u8 = smem;
+            }
+            LaunchScope ls(h, DATMO_TAG_PYRAMID);
+            k_pyr_h<uint8_t><<<g1, 256, smem, h->stream>>>(static_cast<const uint8_t*>(img), T, H, W, L.w, gk, L.ksize,
+                                                           hx, hf, vec);
+        } else {
+            if (smem > configured_f32) {
+                DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_pyr_h<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         static_cast<int>(smem)));
+                configured_f32 = smem;
+            }
+            LaunchScope ls(h, DATMO_TAG_PYRAMID);
+            k_pyr_h<float><<<g1, 256, smem, h->stream>>>(static_cast<const float*>(img), T, H, W, L.w, gk, L.ksize, hx,
+                                                         hf, vec);
+        }
     }
     DATMO_POST_LAUNCH(h);
-    dim3 g2(ceil_div(L.w, 128), L.h, B);
+    dim3 g2(ceil_div(L.w, 128), ceil_div(L.h, PYR_ROWS), B);
     {
         LaunchScope ls(h, DATMO_TAG_PYRAMID);
-        k_pyr_v<<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, d_kern, L.ksize, static_cast<double>(H) / L.h);
+        k_pyr_v<<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, gk, L.ksize, vy, vf);
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
@@ -1596,13 +1727,12 @@ int fb_run(datmo_ctx* h, const void* prev, const void* next, int dtype, int H, i
     std::vector<FbLayer> layers = fb_plan(H, W, p->pyr_scale, p->levels);
     PolyCoef pc;
     DATMO_REQUIRE(h, poly_setup(p->poly_n, p->poly_sigma, pc), "polynomial expansion setup failed");
-    std::vector<float> kern_all;
+    std::vector<float> kern_all;  // per-layer pyramid tables (pyr_tables), concatenated
     std::vector<int> kern_off;
     for (auto& L : layers) {
         DATMO_REQUIRE(h, L.ksize / 2 < std::min(H, W), "image too small for the pyramid smoothing kernel");
         kern_off.push_back(static_cast<int>(kern_all.size()));
-        auto k = gaussian_kernel(L.ksize, L.sigma);
-        kern_all.insert(kern_all.end(), k.begin(), k.end());
+        pyr_tables(H, W, L, kern_all);
     }
     const bool need_M = p->variant == 1;
     // chunk the batch so the workspace stays inside the budget
@@ -1716,17 +1846,18 @@ int datmo_fb_pyramid_image_dev(datmo_handle_t h, const void* img, int dtype, int
     DATMO_ENTER(h);
     DATMO_REQUIRE(h, img && out && H >= 1 && W >= 1 && batch >= 1 && h_out >= 1 && w_out >= 1, "bad arguments");
     DATMO_REQUIRE(h, ksize >= 1 && (ksize & 1) && ksize / 2 < std::min(H, W), "bad ksize");
-    auto k = gaussian_kernel(ksize, sigma);
+    FbLayer L{0, 1.0, sigma, ksize, w_out, h_out};
+    std::vector<float> tab;
+    pyr_tables(H, W, L, tab);
     Bump dry(nullptr);
-    dry.take<float>(ksize);
+    dry.take<float>(tab.size());
     dry.take<float>(static_cast<size_t>(batch) * H * w_out);
     DATMO_TRY(datmo_ws_reserve(h, dry.off));
     Bump bump(h->ws);
-    float* d_k = bump.take<float>(ksize);
+    float* d_k = bump.take<float>(tab.size());
     float* T = bump.take<float>(static_cast<size_t>(batch) * H * w_out);
-    DATMO_CHECK_CUDA(h, cudaMemcpyAsync(d_k, k.data(), ksize * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));  // k is a stack-lifetime vector
-    FbLayer L{0, 1.0, sigma, ksize, w_out, h_out};
+    DATMO_CHECK_CUDA(h, cudaMemcpyAsync(d_k, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));  // tab is a stack-lifetime vector
     return launch_pyr(h, img, dtype, H, W, batch, L, d_k, T, out);
 }
 

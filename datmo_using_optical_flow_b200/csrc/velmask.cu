@@ -7,6 +7,8 @@
 // np.gradient: central difference / 2 in the interior, one-sided first order at the
 // edges, f32 in -> f32 out; the comparison against alpha happens in f32 (numpy's weak
 // python-scalar promotion); v * mask promotes to f64 and the magnitude test runs in f64.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace {
@@ -19,7 +21,7 @@ __device__ __forceinline__ float grad1(float lo, float c, float hi, int i, int n
 }
 
 __global__ void __launch_bounds__(256) k_velmask(const float2* __restrict__ flow, int H, int W, float px, float py,
-                                                 float alpha, double thresh, float* __restrict__ vx_o,
+                                                 float alpha, double s_crit, float* __restrict__ vx_o,
                                                  float* __restrict__ vy_o, float* __restrict__ ang_o,
                                                  uint8_t* __restrict__ mask_o, float* __restrict__ vxf_o,
                                                  float* __restrict__ vyf_o, uint8_t* __restrict__ valid_o,
@@ -44,8 +46,9 @@ __global__ void __launch_bounds__(256) k_velmask(const float2* __restrict__ flow
         const int m = (fabsf(div) <= alpha) && (fabsf(curl) <= alpha);
         const float vxf = m ? vx : 0.f, vyf = m ? vy : 0.f;
         const double dx = vxf, dy = vyf;
-        const double mag = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-        is_valid = mag > thresh;
+        // sqrt is monotone and correctly rounded, so "sqrt(s) > thresh" is "s > s_crit" with s_crit the
+        // largest double whose root is still <= thresh (found on the host): no DSQRT per cell
+        is_valid = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) > s_crit;
         if (vx_o) vx_o[base + o] = vx;
         if (vy_o) vy_o[base + o] = vy;
         if (ang_o) ang_o[base + o] = curl;
@@ -99,11 +102,20 @@ extern "C" int datmo_velocity_mask_dev(datmo_handle_t h, const float* flow, int 
     DATMO_REQUIRE(h, H <= 65535 && batch <= 65535, "H and batch must fit a CUDA grid dimension");
     DATMO_REQUIRE(h, !ang_f || (vx_f && vy_f), "ang_f needs vx_f and vy_f");
     if (n_valid) DATMO_CHECK_CUDA(h, cudaMemsetAsync(n_valid, 0, batch * sizeof(int32_t), h->stream));
+    // largest s with sqrt(s) <= thresh
+    double s_crit = -1.0;
+    if (thresh >= 0) {
+        s_crit = thresh * thresh;
+        while (s_crit > 0 && sqrt(s_crit) > thresh) s_crit = nextafter(s_crit, 0.0);
+        while (sqrt(nextafter(s_crit, INFINITY)) <= thresh) s_crit = nextafter(s_crit, INFINITY);
+    } else if (thresh != thresh) {
+        s_crit = INFINITY;  // NaN threshold: nothing is valid
+    }
     dim3 g(ceil_div(W, 256), H, batch);
     {
         LaunchScope ls(h, DATMO_TAG_VELMASK);
         k_velmask<<<g, 256, 0, h->stream>>>(reinterpret_cast<const float2*>(flow), H, W, static_cast<float>(px_x),
-                                            static_cast<float>(px_y), static_cast<float>(alpha_cont), thresh, vx, vy,
+                                            static_cast<float>(px_y), static_cast<float>(alpha_cont), s_crit, vx, vy,
                                             ang, mask, vx_f, vy_f, valid, n_valid);
     }
     DATMO_POST_LAUNCH(h);
