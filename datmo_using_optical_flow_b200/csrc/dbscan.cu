@@ -23,17 +23,35 @@ constexpr int SCAN_ITEMS = 4096;  // grid cells handled by one CTA of the flag s
 constexpr int SCAN_THREADS = 256;
 
 // ---- generic exclusive scan of uint8 flags over [batch][n] ---------------------------
+// Each thread owns 16 consecutive flags, fetched with one 16-byte load when the frame is
+// 16-byte aligned (n % 16 == 0 and an aligned base); bit k of the result = flag k is non-zero.
+__device__ __forceinline__ unsigned load_flags16(const uint8_t* __restrict__ f, int64_t p0, int64_t n, bool vec) {
+    unsigned bits = 0;
+    if (vec && p0 + 16 <= n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(f + p0);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned m = __vcmpne4(w[j], 0u);  // 0xff per non-zero byte
+            bits |= ((m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u)) << (4 * j);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (p0 + i < n && f[p0 + i] != 0) bits |= 1u << i;
+    }
+    return bits;
+}
+
 // pass 1: per-CTA totals
 __global__ void __launch_bounds__(SCAN_THREADS) k_flag_block_sums(const uint8_t* __restrict__ flags, int64_t n,
-                                                                  int nblk, int32_t* __restrict__ block_sums) {
+                                                                  int nblk, int32_t* __restrict__ block_sums,
+                                                                  int vec) {
     const int blk = blockIdx.x, b = blockIdx.y;
     const uint8_t* f = flags + static_cast<size_t>(b) * n;
-    int64_t start = static_cast<int64_t>(blk) * SCAN_ITEMS;
-    int cnt = 0;
-    for (int i = threadIdx.x; i < SCAN_ITEMS; i += SCAN_THREADS) {
-        int64_t p = start + i;
-        cnt += (p < n) ? (f[p] != 0) : 0;
-    }
+    static_assert(SCAN_ITEMS == 16 * SCAN_THREADS, "one 16-flag group per thread");
+    const int64_t p0 = static_cast<int64_t>(blk) * SCAN_ITEMS + static_cast<int64_t>(threadIdx.x) * 16;
+    int cnt = p0 < n ? __popc(load_flags16(f, p0, n, vec != 0)) : 0;
     __shared__ int s_w[SCAN_THREADS / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
@@ -80,21 +98,15 @@ __global__ void __launch_bounds__(256) k_scan_block_sums(int32_t* __restrict__ b
 // pass 3: exclusive rank of every flagged cell (others get -1)
 __global__ void __launch_bounds__(SCAN_THREADS) k_flag_ranks(const uint8_t* __restrict__ flags, int64_t n, int nblk,
                                                              const int32_t* __restrict__ block_offs,
-                                                             int32_t* __restrict__ rank, int sparse) {
+                                                             int32_t* __restrict__ rank, int sparse, int vec) {
     const int blk = blockIdx.x, b = blockIdx.y;
     const uint8_t* f = flags + static_cast<size_t>(b) * n;
     int32_t* r = rank + static_cast<size_t>(b) * n;
-    const int64_t start = static_cast<int64_t>(blk) * SCAN_ITEMS;
     constexpr int PER = SCAN_ITEMS / SCAN_THREADS;  // contiguous cells per thread
-    const int64_t p0 = start + static_cast<int64_t>(threadIdx.x) * PER;
-    int local[PER];
-    int cnt = 0;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        int64_t p = p0 + i;
-        local[i] = (p < n) ? (f[p] != 0) : 0;
-        cnt += local[i];
-    }
+    static_assert(PER == 16, "one 16-flag group per thread");
+    const int64_t p0 = static_cast<int64_t>(blk) * SCAN_ITEMS + static_cast<int64_t>(threadIdx.x) * PER;
+    const unsigned bits = p0 < n ? load_flags16(f, p0, n, vec != 0) : 0u;
+    const int cnt = __popc(bits);
     // CTA-wide exclusive scan of cnt
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int inc = cnt;
@@ -109,39 +121,55 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_flag_ranks(const uint8_t* __re
     int woff = 0;
     for (int i = 0; i < wid; ++i) woff += s_w[i];
     int run = block_offs[static_cast<size_t>(b) * nblk + blk] + woff + inc - cnt;
+    if (sparse) {
+        // only flagged cells are ever looked up: skip the 4 B/cell fill
+        unsigned rem = bits;
+        while (rem) {
+            const int i = __ffs(rem) - 1;
+            rem &= rem - 1;
+            r[p0 + i] = run++;
+        }
+    } else {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        int64_t p = p0 + i;
-        if (p < n) {
-            // sparse: only flagged cells are ever looked up, skip the 4 B/cell fill
-            if (local[i])
-                r[p] = run;
-            else if (!sparse)
-                r[p] = -1;
-            run += local[i];
+        for (int i = 0; i < PER; ++i) {
+            if (p0 + i < n) {
+                const int on = (bits >> i) & 1;
+                r[p0 + i] = on ? run : -1;
+                run += on;
+            }
         }
     }
 }
 
 // ---- neighbour predicate ----------------------------------------------------------------
-__device__ __forceinline__ bool within_eps(int dr, int dc, float vx0, float vy0, float vx1, float vy1, double eps2) {
+// eps^2 with an f32 guard band: the f32 evaluation of d2 is within 3e-7 (relative) of the fp64 one,
+// so outside [lo, hi] = eps^2 (1 -+ 2e-6) it decides; only the sliver in between pays for fp64.
+struct EpsTest {
+    double e2;
+    float lo, hi;
+};
+
+__device__ __forceinline__ bool within_eps(int dr, int dc, float vx0, float vy0, float vx1, float vy1,
+                                           const EpsTest& e) {
+    const float fvx = vx0 - vx1, fvy = vy0 - vy1;
+    const float s = static_cast<float>(dr * dr + dc * dc) + fvx * fvx + fvy * fvy;
+    if (s < e.lo) return true;
+    if (s > e.hi) return false;
     double d2 = static_cast<double>(dr * dr);
     d2 = __dadd_rn(d2, static_cast<double>(dc * dc));
     const double dvx = __dsub_rn(static_cast<double>(vx0), static_cast<double>(vx1));
     const double dvy = __dsub_rn(static_cast<double>(vy0), static_cast<double>(vy1));
     d2 = __dadd_rn(d2, __dmul_rn(dvx, dvx));
     d2 = __dadd_rn(d2, __dmul_rn(dvy, dvy));
-    return d2 <= eps2;
+    return d2 <= e.e2;
 }
 
 // state: 0 = not valid, 1 = valid non-core, 2 = core.  parent: self for core cells, -1 otherwise.
-__global__ void __launch_bounds__(256) k_core(const float* __restrict__ vx, const float* __restrict__ vy,
-                                              const uint8_t* __restrict__ valid, int H, int W, int r, double eps2,
+__device__ __forceinline__ void core_cell(int x, int y, int b, const float* __restrict__ vx, const float* __restrict__ vy,
+                                              const uint8_t* __restrict__ valid, int H, int W, int r, EpsTest eps2,
                                               int min_samples, uint8_t* __restrict__ state,
                                               int32_t* __restrict__ parent) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
+
     const size_t base = static_cast<size_t>(b) * H * W;
     const int o = y * W + x;
     uint8_t st = 0;
@@ -151,14 +179,24 @@ __global__ void __launch_bounds__(256) k_core(const float* __restrict__ vx, cons
         // reaches min_samples; only otherwise count over the whole window
         int cnt = 1;  // self
         if (r >= 1 && cnt < min_samples) {
+            // all four flags, then all four velocity pairs: two load latencies instead of eight
             const int ndr[4] = {0, 0, -1, 1}, ndc[4] = {-1, 1, 0, 0};
+            bool on[4];
+            float nvx[4], nvy[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int yy = y + ndr[k], xx = x + ndc[k];
-                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                const size_t q = base + static_cast<size_t>(yy) * W + xx;
-                if (valid[q] && within_eps(ndr[k], ndc[k], vx0, vy0, vx[q], vy[q], eps2)) ++cnt;
+                on[k] = yy >= 0 && yy < H && xx >= 0 && xx < W && valid[base + static_cast<size_t>(yy) * W + xx];
             }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const size_t q = base + static_cast<size_t>(y + ndr[k]) * W + (x + ndc[k]);
+                nvx[k] = on[k] ? vx[q] : 0.f;
+                nvy[k] = on[k] ? vy[q] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (on[k] && within_eps(ndr[k], ndc[k], vx0, vy0, nvx[k], nvy[k], eps2)) ++cnt;
         }
         if (cnt < min_samples) cnt = 0;  // inconclusive: recount exactly
         for (int dr = -r; dr <= r && cnt < min_samples; ++dr) {
@@ -177,6 +215,30 @@ __global__ void __launch_bounds__(256) k_core(const float* __restrict__ vx, cons
     }
     state[base + o] = st;
     parent[base + o] = st == 2 ? o : -1;
+}
+
+// Thread-per-cell kernels of this file handle FOUR consecutive cells per thread: one vector load
+// tells whether any of them has work (four in five do not), which quarters the number of CTAs the
+// GPU has to turn over — with one cell per thread that turnover, not memory, was the bound.
+__device__ __forceinline__ bool vec4_ok(int W, const void* p) {
+    return (W & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+
+__global__ void __launch_bounds__(256) k_core(const float* __restrict__ vx, const float* __restrict__ vy,
+                                              const uint8_t* __restrict__ valid, int H, int W, int r, EpsTest eps2,
+                                              int min_samples, uint8_t* __restrict__ state,
+                                              int32_t* __restrict__ parent) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x4 >= W) return;
+    const size_t o4 = (static_cast<size_t>(b) * H + y) * W + x4;
+    if (vec4_ok(W, valid) && vec4_ok(W, state) && vec4_ok(W, parent) &&
+        *reinterpret_cast<const unsigned*>(valid + o4) == 0u) {
+        *reinterpret_cast<unsigned*>(state + o4) = 0u;
+        *reinterpret_cast<int4*>(parent + o4) = make_int4(-1, -1, -1, -1);
+        return;
+    }
+    for (int j = 0; j < 4 && x4 + j < W; ++j) core_cell(x4 + j, y, b, vx, vy, valid, H, W, r, eps2, min_samples, state, parent);
 }
 
 // Union-find over int32 cell indices.  Other CTAs link roots concurrently, and L1 is not
@@ -218,41 +280,58 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
 // column, which chain to its first cell).  Linking to the first cell of the whole half-window
 // instead was measured slower: its chains stride (-4,-2) and stay interleaved, leaving several
 // trees per region and defeating the quick reject of pass 2.
-__global__ void __launch_bounds__(256) k_link_near(const float* __restrict__ vx, const float* __restrict__ vy,
+__device__ __forceinline__ void link_near_cell(int x, int y, int b, const float* __restrict__ vx, const float* __restrict__ vy,
                                                    const uint8_t* __restrict__ state, int H, int W, int r,
-                                                   double eps2, int32_t* __restrict__ parent) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, b = blockIdx.z;
-    if (x >= W || r < 1) return;
+                                                   EpsTest eps2, int32_t* __restrict__ parent) {
+
     const size_t base = static_cast<size_t>(b) * H * W;
     const int o = y * W + x;
     if (state[base + o] != 2) return;
     const float vx0 = vx[base + o], vy0 = vy[base + o];
     int best = o;
-    // ascending index order: (-1,-1), (-1,0), (-1,+1), (0,-1); keep the first hit
+    // ascending index order: (-1,-1), (-1,0), (-1,+1), (0,-1); keep the first hit.  States first,
+    // then the velocities of the core ones: independent loads, two latencies in all.
     const int ndr[4] = {-1, -1, -1, 0}, ndc[4] = {-1, 0, 1, -1};
+    bool on[4];
+    float nvx[4], nvy[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int yy = y + ndr[k], xx = x + ndc[k];
-        if (yy < 0 || xx < 0 || xx >= W) continue;
-        const int q = yy * W + xx;
-        if (q < best && state[base + q] == 2 &&
-            within_eps(ndr[k], ndc[k], vx0, vy0, vx[base + q], vy[base + q], eps2))
-            best = q;
+        on[k] = yy >= 0 && xx >= 0 && xx < W && state[base + yy * W + xx] == 2;
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int q = (y + ndr[k]) * W + x + ndc[k];
+        nvx[k] = on[k] ? vx[base + q] : 0.f;
+        nvy[k] = on[k] ? vy[base + q] : 0.f;
+    }
+#pragma unroll
+    for (int k = 3; k >= 0; --k)
+        if (on[k] && within_eps(ndr[k], ndc[k], vx0, vy0, nvx[k], nvy[k], eps2)) best = (y + ndr[k]) * W + x + ndc[k];
     parent[base + o] = best;
+}
+
+__global__ void __launch_bounds__(256) k_link_near(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                   const uint8_t* __restrict__ state, int H, int W, int r,
+                                                   EpsTest eps2, int32_t* __restrict__ parent) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x4 >= W || r < 1) return;
+    if (vec4_ok(W, state)) {
+        const unsigned st4 = *reinterpret_cast<const unsigned*>(state + (static_cast<size_t>(b) * H + y) * W + x4);
+        if ((st4 & 0x02020202u) == 0u) return;  // no core cell among the four
+    }
+    for (int j = 0; j < 4 && x4 + j < W; ++j) link_near_cell(x4 + j, y, b, vx, vy, state, H, W, r, eps2, parent);
 }
 
 // Link pass 1b (after a flatten): the atomics-free pass leaves an 8-connected region split
 // into a few diagonal stripes (one per ragged top / left edge cell).  Join them: same four
 // neighbours, but now "same flattened parent" skips the pair, so only cells ON a stripe
 // interface reach the atomic path.  Afterwards trees == 8-connected regions of close cells.
-__global__ void __launch_bounds__(256) k_union_near(const float* __restrict__ vx, const float* __restrict__ vy,
+__device__ __forceinline__ void union_near_cell(int x, int y, int b, const float* __restrict__ vx, const float* __restrict__ vy,
                                                     const uint8_t* __restrict__ state, int H, int W, int r,
-                                                    double eps2, int32_t* __restrict__ parent) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, b = blockIdx.z;
-    if (x >= W || r < 1) return;
+                                                    EpsTest eps2, int32_t* __restrict__ parent) {
+
     const size_t base = static_cast<size_t>(b) * H * W;
     const int o = y * W + x;
     if (state[base + o] != 2) return;
@@ -261,18 +340,42 @@ __global__ void __launch_bounds__(256) k_union_near(const float* __restrict__ vx
     int joined = -1;
     const float vx0 = vx[base + o], vy0 = vy[base + o];
     const int ndr[4] = {-1, -1, -1, 0}, ndc[4] = {-1, 0, 1, -1};
+    // the four neighbours' parents in one go; velocities only for those in a different tree
+    int pq[4];
+    float nvx[4], nvy[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int yy = y + ndr[k], xx = x + ndc[k];
-        if (yy < 0 || xx < 0 || xx >= W) continue;
-        const int q = yy * W + xx;
-        const int pq = par[q];
-        if (pq < 0 || pq == my_root || pq == joined) continue;
-        if (within_eps(ndr[k], ndc[k], vx0, vy0, vx[base + q], vy[base + q], eps2)) {
-            uf_union(par, o, q);
-            joined = pq;
+        pq[k] = (yy >= 0 && xx >= 0 && xx < W) ? par[yy * W + xx] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool want = pq[k] >= 0 && pq[k] != my_root;
+        const int q = (y + ndr[k]) * W + x + ndc[k];
+        nvx[k] = want ? vx[base + q] : 0.f;
+        nvy[k] = want ? vy[base + q] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (pq[k] < 0 || pq[k] == my_root || pq[k] == joined) continue;
+        if (within_eps(ndr[k], ndc[k], vx0, vy0, nvx[k], nvy[k], eps2)) {
+            uf_union(par, o, (y + ndr[k]) * W + x + ndc[k]);
+            joined = pq[k];
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_union_near(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                    const uint8_t* __restrict__ state, int H, int W, int r,
+                                                    EpsTest eps2, int32_t* __restrict__ parent) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x4 >= W || r < 1) return;
+    if (vec4_ok(W, state)) {
+        const unsigned st4 = *reinterpret_cast<const unsigned*>(state + (static_cast<size_t>(b) * H + y) * W + x4);
+        if ((st4 & 0x02020202u) == 0u) return;
+    }
+    for (int j = 0; j < 4 && x4 + j < W; ++j) union_near_cell(x4 + j, y, b, vx, vy, state, H, W, r, eps2, parent);
 }
 
 // Link pass 2 (after a flatten): the whole preceding half-window.  parent[] now holds each
@@ -281,7 +384,7 @@ __global__ void __launch_bounds__(256) k_union_near(const float* __restrict__ vx
 // pass-1 trees reach the atomic path.
 __global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx, const float* __restrict__ vy,
                                                    const uint8_t* __restrict__ state, int H, int W, int r,
-                                                   double eps2, int32_t* __restrict__ parent) {
+                                                   EpsTest eps2, int32_t* __restrict__ parent) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z;
     const size_t base = static_cast<size_t>(b) * H * W;
@@ -384,14 +487,12 @@ __global__ void __launch_bounds__(256) k_flatten(int64_t n, int32_t* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) k_labels(const float* __restrict__ vx, const float* __restrict__ vy,
+__device__ __forceinline__ void labels_cell(int x, int y, int b, const float* __restrict__ vx, const float* __restrict__ vy,
                                                 const uint8_t* __restrict__ state, const int32_t* __restrict__ parent,
                                                 const int32_t* __restrict__ rank, const int32_t* __restrict__ root_rank,
-                                                int H, int W, int r, double eps2, int cap,
+                                                int H, int W, int r, EpsTest eps2, int cap,
                                                 int32_t* __restrict__ labels, int32_t* __restrict__ indices) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
+
     const size_t base = static_cast<size_t>(b) * H * W;
     const int o = y * W + x;
     const uint8_t st = state[base + o];
@@ -423,6 +524,20 @@ __global__ void __launch_bounds__(256) k_labels(const float* __restrict__ vx, co
     indices[2 * out + 1] = x;
 }
 
+__global__ void __launch_bounds__(256) k_labels(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                const uint8_t* __restrict__ state, const int32_t* __restrict__ parent,
+                                                const int32_t* __restrict__ rank, const int32_t* __restrict__ root_rank,
+                                                int H, int W, int r, EpsTest eps2, int cap,
+                                                int32_t* __restrict__ labels, int32_t* __restrict__ indices) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x4 >= W) return;
+    if (vec4_ok(W, state) && *reinterpret_cast<const unsigned*>(state + (static_cast<size_t>(b) * H + y) * W + x4) == 0u)
+        return;  // no valid cell among the four
+    for (int j = 0; j < 4 && x4 + j < W; ++j)
+        labels_cell(x4 + j, y, b, vx, vy, state, parent, rank, root_rank, H, W, r, eps2, cap, labels, indices);
+}
+
 static int dbg_tag(int sub) {
     // DATMO_DBSCAN_SUBTAGS=1 spreads the DBSCAN kernels over the other profiler tags (tools/dbscan_prof.py)
     static const bool on = getenv("DATMO_DBSCAN_SUBTAGS") != nullptr;
@@ -436,9 +551,10 @@ int datmo_flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, in
                     int32_t* rank, int tag, int sparse) {
     int nblk = static_cast<int>(ceil_div64(n, SCAN_ITEMS));
     dim3 g(nblk, batch);
+    const int vec = (n & 15) == 0 && (reinterpret_cast<uintptr_t>(flags) & 15) == 0;
     {
         LaunchScope ls(h, tag);
-        k_flag_block_sums<<<g, SCAN_THREADS, 0, h->stream>>>(flags, n, nblk, block_sums);
+        k_flag_block_sums<<<g, SCAN_THREADS, 0, h->stream>>>(flags, n, nblk, block_sums, vec);
     }
     DATMO_POST_LAUNCH(h);
     {
@@ -448,7 +564,7 @@ int datmo_flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, in
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, tag);
-        k_flag_ranks<<<g, SCAN_THREADS, 0, h->stream>>>(flags, n, nblk, block_sums, rank, sparse);
+        k_flag_ranks<<<g, SCAN_THREADS, 0, h->stream>>>(flags, n, nblk, block_sums, rank, sparse, vec);
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
@@ -471,7 +587,7 @@ __global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__
     const int n = min(n_valid[b], cap);
     if (static_cast<int>(blockIdx.x * blockDim.x) >= n) return;  // whole CTA past the end
     int lab = -1;
-    unsigned long long r = 0, c = 0;
+    unsigned r = 0, c = 0;
     double fvx = 0.0, fvy = 0.0;
     if (i < n) {
         const size_t o = static_cast<size_t>(b) * cap + i;
@@ -483,47 +599,31 @@ __global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__
             fvx = vx[p], fvy = vy[p];
         }
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, lab);
+    // Compact cells are row-major, so a warp holds a few RUNS of equal labels.  Segmented inclusive
+    // scan over the runs (5 shuffle steps for any mix of labels); the last lane of a run then holds
+    // its totals and issues the atomics.  A label split over several runs simply adds several times.
     const int lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    unsigned long long sr, sc, srr, src, scc;
-    double svx, svy;
-    if (peers == 0xffffffffu) {
-        // the usual case — the whole warp sits in one cluster: butterfly reduction
-        sr = r, sc = c, srr = r * r, src = r * c, scc = c * c;
-        svx = fvx, svy = fvy;
+    const int prev = __shfl_up_sync(0xffffffffu, lab, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != lab);
+    const int seg0 = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));  // first lane of my run
+    unsigned sr = r, sc = c;  // <= 32 * 65535: fits
+    unsigned long long srr = static_cast<unsigned long long>(r) * r, src = static_cast<unsigned long long>(r) * c,
+                       scc = static_cast<unsigned long long>(c) * c;
+    double svx = fvx, svy = fvy;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sr += __shfl_xor_sync(0xffffffffu, sr, o);
-            sc += __shfl_xor_sync(0xffffffffu, sc, o);
-            srr += __shfl_xor_sync(0xffffffffu, srr, o);
-            src += __shfl_xor_sync(0xffffffffu, src, o);
-            scc += __shfl_xor_sync(0xffffffffu, scc, o);
-            svx += __shfl_xor_sync(0xffffffffu, svx, o);
-            svy += __shfl_xor_sync(0xffffffffu, svy, o);
-        }
-    } else {
-        sr = sc = srr = src = scc = 0;
-        svx = svy = 0.0;
-        unsigned rem = peers;
-        while (__any_sync(0xffffffffu, rem != 0)) {
-            const int src_lane = rem ? __ffs(rem) - 1 : 0;
-            const unsigned long long tr = __shfl_sync(0xffffffffu, r, src_lane);
-            const unsigned long long tc = __shfl_sync(0xffffffffu, c, src_lane);
-            const double tvx = __shfl_sync(0xffffffffu, fvx, src_lane);
-            const double tvy = __shfl_sync(0xffffffffu, fvy, src_lane);
-            if (rem) {
-                sr += tr, sc += tc, srr += tr * tr, src += tr * tc, scc += tc * tc;
-                svx += tvx, svy += tvy;
-                rem &= rem - 1;
-            }
-        }
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned tr = __shfl_up_sync(0xffffffffu, sr, d), tc = __shfl_up_sync(0xffffffffu, sc, d);
+        const unsigned long long trr = __shfl_up_sync(0xffffffffu, srr, d), trc = __shfl_up_sync(0xffffffffu, src, d),
+                                 tcc = __shfl_up_sync(0xffffffffu, scc, d);
+        const double tvx = __shfl_up_sync(0xffffffffu, svx, d), tvy = __shfl_up_sync(0xffffffffu, svy, d);
+        if (lane - d >= seg0) sr += tr, sc += tc, srr += trr, src += trc, scc += tcc, svx += tvx, svy += tvy;
     }
-    if (lane == leader && lab >= 0) {
+    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    if (tail && lab >= 0) {
         unsigned long long* a = acc + (static_cast<size_t>(b) * max_clusters + lab) * 8;
-        atomicAdd(a + 0, static_cast<unsigned long long>(__popc(peers)));
-        atomicAdd(a + 1, sr);
-        atomicAdd(a + 2, sc);
+        atomicAdd(a + 0, static_cast<unsigned long long>(lane - seg0 + 1));
+        atomicAdd(a + 1, static_cast<unsigned long long>(sr));
+        atomicAdd(a + 2, static_cast<unsigned long long>(sc));
         atomicAdd(reinterpret_cast<double*>(a + 3), svx);
         atomicAdd(reinterpret_cast<double*>(a + 4), svy);
         atomicAdd(a + 5, srr);
@@ -573,7 +673,10 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
     const int64_t n = static_cast<int64_t>(H) * W;
     const int nblk = static_cast<int>(ceil_div64(n, SCAN_ITEMS));
     const int r = static_cast<int>(floor(eps));
-    const double eps2 = eps * eps;
+    EpsTest eps2;
+    eps2.e2 = eps * eps;
+    eps2.lo = static_cast<float>(eps2.e2 * (1.0 - 2e-6));
+    eps2.hi = static_cast<float>(eps2.e2 * (1.0 + 2e-6));
     size_t total;
     uint8_t *state, *is_root;
     int32_t *parent, *rank, *root_rank, *bsum, *ncl;
@@ -591,39 +694,42 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
     }
     DATMO_TRY(datmo_flag_scan(h, valid, n, batch, bsum, n_valid, rank, dbg_tag(0), 1));
     dim3 g(ceil_div(W, 256), H, batch);
-    {
-        LaunchScope ls(h, dbg_tag(1));
-        k_core<<<g, 256, 0, h->stream>>>(vx_f, vy_f, valid, H, W, r, eps2, min_samples, state, parent);
-    }
-    DATMO_POST_LAUNCH(h);
+    dim3 g4(ceil_div(W, 1024), H, batch);  // four cells per thread
     dim3 gf(static_cast<unsigned>(ceil_div64(n, 1024)), batch);
-    if (r >= 1) {
+    {
         {
-            LaunchScope ls(h, dbg_tag(2));
-            k_link_near<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+            LaunchScope ls(h, dbg_tag(1));
+            k_core<<<g4, 256, 0, h->stream>>>(vx_f, vy_f, valid, H, W, r, eps2, min_samples, state, parent);
         }
         DATMO_POST_LAUNCH(h);
-        {
-            LaunchScope ls(h, dbg_tag(3));
-            k_flatten<false><<<gf, 256, 0, h->stream>>>(n, parent, is_root);
-        }
-        DATMO_POST_LAUNCH(h);
-        {
-            LaunchScope ls(h, dbg_tag(5));
-            k_union_near<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
-        }
-        DATMO_POST_LAUNCH(h);
-        if (r > 1) {
+        if (r >= 1) {
+            {
+                LaunchScope ls(h, dbg_tag(2));
+                k_link_near<<<g4, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+            }
+            DATMO_POST_LAUNCH(h);
             {
                 LaunchScope ls(h, dbg_tag(3));
                 k_flatten<false><<<gf, 256, 0, h->stream>>>(n, parent, is_root);
             }
             DATMO_POST_LAUNCH(h);
             {
-                LaunchScope ls(h, dbg_tag(4));
-                k_union_far<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+                LaunchScope ls(h, dbg_tag(5));
+                k_union_near<<<g4, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
             }
             DATMO_POST_LAUNCH(h);
+            if (r > 1) {
+                {
+                    LaunchScope ls(h, dbg_tag(3));
+                    k_flatten<false><<<gf, 256, 0, h->stream>>>(n, parent, is_root);
+                }
+                DATMO_POST_LAUNCH(h);
+                {
+                    LaunchScope ls(h, dbg_tag(4));
+                    k_union_far<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);
+                }
+                DATMO_POST_LAUNCH(h);
+            }
         }
     }
     {
@@ -635,7 +741,7 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
     DATMO_TRY(datmo_flag_scan(h, is_root, n, batch, bsum, ncl_out, root_rank, dbg_tag(0), 1));
     {
         LaunchScope ls(h, dbg_tag(6));
-        k_labels<<<g, 256, 0, h->stream>>>(vx_f, vy_f, state, parent, rank, root_rank, H, W, r, eps2, cap, labels,
+        k_labels<<<g4, 256, 0, h->stream>>>(vx_f, vy_f, state, parent, rank, root_rank, H, W, r, eps2, cap, labels,
                                            indices);
     }
     DATMO_POST_LAUNCH(h);

@@ -132,6 +132,32 @@ void pyr_tables(int H, int W, const FbLayer& L, std::vector<float>& out) {
     memcpy(gk, g.data(), sizeof(float) * L.ksize);
 }
 
+// Tables of one flow upsampling step (wi x hi -> wo x ho), appended to `out` as 32-bit words:
+//   sx [wo] int | fx [wo] float | sy [ho] int | fy [ho] float
+size_t up_table_words(int wo, int ho) { return 2 * static_cast<size_t>(wo + ho); }
+
+void up_tables(int hi, int wi, int ho, int wo, std::vector<float>& out) {
+    const size_t base = out.size();
+    out.resize(base + up_table_words(wo, ho), 0.f);
+    float* sx = out.data() + base;
+    float* fx = sx + wo;
+    float* sy = fx + wo;
+    float* fy = sy + ho;
+    auto fill = [&](int n_out, int n_src, float* first, float* frac) {
+        const double ratio = static_cast<double>(n_src) / n_out;
+        for (int d = 0; d < n_out; ++d) {
+            int sidx;
+            double f;
+            resize_tap_host(d, n_src, ratio, sidx, f);
+            const int32_t i32 = sidx;
+            memcpy(first + d, &i32, sizeof(int32_t));
+            frac[d] = static_cast<float>(f);
+        }
+    };
+    fill(wo, wi, sx, fx);
+    fill(ho, hi, sy, fy);
+}
+
 constexpr int POLY_MAX_N = 16;
 struct PolyCoef {
     float g[POLY_MAX_N + 1], xg[POLY_MAX_N + 1], xxg[POLY_MAX_N + 1];
@@ -586,30 +612,49 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp(const SrcT* __restr
 // ------------------------------------------------------------------------------------
 // F3: flow initialisation of a finer layer = bilinear resize of the coarser flow * mul
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_upsample_flow(const float2* __restrict__ fin, float2* __restrict__ fout,
-                                                       int hi, int wi, int ho, int wo, double rx, double ry,
-                                                       double mul) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y, b = blockIdx.z;
+// Source taps and weights come from per-layer tables (up_tables): the fp64 tap arithmetic that
+// decides which texels are read runs once per column / row on the host, not per pixel.
+// A thread produces UP_ROWS rows x 2 columns (one 16-byte store per row): few, fat CTAs — a CTA per
+// 128 single-pixel threads spent its life waiting for one dependent load.
+constexpr int UP_ROWS = 4;
+__global__ void __launch_bounds__(256) k_upsample_flow(const float2* __restrict__ fin, float2* __restrict__ fout,
+                                                       int hi, int wi, int ho, int wo, const int* __restrict__ sxt,
+                                                       const float* __restrict__ fxt, const int* __restrict__ syt,
+                                                       const float* __restrict__ fyt, float fmul) {
+    const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int y0 = blockIdx.y * UP_ROWS, b = blockIdx.z;
     if (x >= wo) return;
-    int sx, sy;
-    double fx, fy;
-    resize_tap(x, wi, rx, sx, fx);
-    resize_tap(y, hi, ry, sy, fy);
-    int sx1 = min(sx + 1, wi - 1), sy1 = min(sy + 1, hi - 1);
+    const bool two = x + 1 < wo;
+    const int xb = two ? x + 1 : x;
+    const int sxa = sxt[x], sxb = sxt[xb];
+    const int sxa1 = min(sxa + 1, wi - 1), sxb1 = min(sxb + 1, wi - 1);
+    const float ga1 = fxt[x], ga0 = 1.f - ga1, gb1 = fxt[xb], gb0 = 1.f - gb1;
     const float2* p = fin + static_cast<size_t>(b) * hi * wi;
-    float2 a = p[static_cast<size_t>(sy) * wi + sx], bb = p[static_cast<size_t>(sy) * wi + sx1];
-    float2 c = p[static_cast<size_t>(sy1) * wi + sx], d = p[static_cast<size_t>(sy1) * wi + sx1];
-    // tap index / fraction in fp64 (they decide which texels are read); the interpolation itself in
-    // f32 — horizontal pass rounded to f32, then vertical, as cv::resize does
-    const float gx1 = static_cast<float>(fx), gx0 = 1.f - gx1, gy1 = static_cast<float>(fy), gy0 = 1.f - gy1;
-    const float t0x = gx0 * a.x + gx1 * bb.x, t0y = gx0 * a.y + gx1 * bb.y;
-    const float t1x = gx0 * c.x + gx1 * d.x, t1y = gx0 * c.y + gx1 * d.y;
-    const float fmul = static_cast<float>(mul);
-    float2 o;
-    o.x = (gy0 * t0x + gy1 * t1x) * fmul;
-    o.y = (gy0 * t0y + gy1 * t1y) * fmul;
-    fout[(static_cast<size_t>(b) * ho + y) * wo + x] = o;
+    float2* o = fout + (static_cast<size_t>(b) * ho + y0) * wo + x;
+    const bool vec = two && (wo & 1) == 0;  // 16-byte aligned pair
+#pragma unroll
+    for (int rr = 0; rr < UP_ROWS; ++rr, o += wo) {
+        const int y = y0 + rr;
+        if (y >= ho) break;
+        const int sy = syt[y], sy1 = min(sy + 1, hi - 1);
+        const float gy1 = fyt[y], gy0 = 1.f - gy1;
+        const float2* r0 = p + sy * wi;
+        const float2* r1 = p + sy1 * wi;
+        // the interpolation itself in f32 — horizontal pass rounded to f32, then vertical, as cv::resize does
+        const float2 a = r0[sxa], a1 = r0[sxa1], c = r1[sxa], c1 = r1[sxa1];
+        const float2 e = r0[sxb], e1 = r0[sxb1], g = r1[sxb], g1 = r1[sxb1];
+        float2 oa, ob;
+        oa.x = (gy0 * (ga0 * a.x + ga1 * a1.x) + gy1 * (ga0 * c.x + ga1 * c1.x)) * fmul;
+        oa.y = (gy0 * (ga0 * a.y + ga1 * a1.y) + gy1 * (ga0 * c.y + ga1 * c1.y)) * fmul;
+        ob.x = (gy0 * (gb0 * e.x + gb1 * e1.x) + gy1 * (gb0 * g.x + gb1 * g1.x)) * fmul;
+        ob.y = (gy0 * (gb0 * e.y + gb1 * e1.y) + gy1 * (gb0 * g.y + gb1 * g1.y)) * fmul;
+        if (vec) {
+            *reinterpret_cast<float4*>(o) = make_float4(oa.x, oa.y, ob.x, ob.y);
+        } else {
+            o[0] = oa;
+            if (two) o[1] = ob;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -1570,13 +1615,17 @@ int launch_update_matrices(datmo_ctx* h, const float* R0, const float* R1, const
     return DATMO_OK;
 }
 
-int launch_upsample(datmo_ctx* h, const float* fin, int hi, int wi, float* fout, int ho, int wo, int B, double mul) {
-    dim3 g(ceil_div(wo, 128), ho, B);
+int launch_upsample(datmo_ctx* h, const float* fin, int hi, int wi, float* fout, int ho, int wo, int B, double mul,
+                    const float* d_tab) {
+    const int* sx = reinterpret_cast<const int*>(d_tab);
+    const float* fx = d_tab + wo;
+    const int* sy = reinterpret_cast<const int*>(fx + wo);
+    const float* fy = fx + wo + ho;
+    dim3 g(ceil_div(wo, 512), ceil_div(ho, UP_ROWS), B);
     {
         LaunchScope ls(h, DATMO_TAG_FLOW_INIT);
-        k_upsample_flow<<<g, 128, 0, h->stream>>>(reinterpret_cast<const float2*>(fin), reinterpret_cast<float2*>(fout),
-                                                  hi, wi, ho, wo, static_cast<double>(wi) / wo,
-                                                  static_cast<double>(hi) / ho, mul);
+        k_upsample_flow<<<g, 256, 0, h->stream>>>(reinterpret_cast<const float2*>(fin), reinterpret_cast<float2*>(fout),
+                                                  hi, wi, ho, wo, sx, fx, sy, fy, static_cast<float>(mul));
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
@@ -1664,7 +1713,8 @@ size_t fb_carve(Bump& bump, FbWorkspace& ws, int H, int W, int B, int n_kern, bo
 
 int fb_run_chunk(datmo_ctx* h, const void* prev, const void* next, int dtype, int H, int W, int B,
                  const datmo_farneback_params& p, const std::vector<FbLayer>& layers, const PolyCoef& pc,
-                 const FbWorkspace& ws, const std::vector<int>& kern_off, float* flow_out) {
+                 const FbWorkspace& ws, const std::vector<int>& kern_off, const std::vector<int>& up_off,
+                 float* flow_out) {
     float* cur = nullptr;  // flow of the layer just finished
     int cur_w = 0, cur_h = 0;
     const bool fused = p.variant != 1;
@@ -1693,7 +1743,7 @@ int fb_run_chunk(datmo_ctx* h, const void* prev, const void* next, int dtype, in
         } else {
             fin = cur == ws.flowA ? ws.flowB : ws.flowA;
             fout = cur;
-            DATMO_TRY(launch_upsample(h, cur, cur_h, cur_w, fin, L.h, L.w, B, 1.0 / p.pyr_scale));
+            DATMO_TRY(launch_upsample(h, cur, cur_h, cur_w, fin, L.h, L.w, B, 1.0 / p.pyr_scale, ws.kern + up_off[li]));
         }
         for (int it = 0; it < p.iterations; ++it) {
             float* dst = (last_layer && it == p.iterations - 1) ? flow_out : fout;
@@ -1734,6 +1784,12 @@ int fb_run(datmo_ctx* h, const void* prev, const void* next, int dtype, int H, i
         kern_off.push_back(static_cast<int>(kern_all.size()));
         pyr_tables(H, W, L, kern_all);
     }
+    std::vector<int> up_off(layers.size(), 0);  // flow upsampling tables of the step INTO layer li
+    for (size_t li = 1; li < layers.size(); ++li) {
+        up_off[li] = static_cast<int>(kern_all.size());
+        up_tables(layers[li - 1].h, layers[li - 1].w, layers[li].h, layers[li].w, kern_all);
+        if (kern_all.size() & 1) kern_all.push_back(0.f);  // pyramid tables must start 8-byte aligned
+    }
     const bool need_M = p->variant == 1;
     // chunk the batch so the workspace stays inside the budget
     FbWorkspace ws;
@@ -1764,7 +1820,7 @@ int fb_run(datmo_ctx* h, const void* prev, const void* next, int dtype, int H, i
         int B = std::min(chunk, batch - b0);
         DATMO_TRY(fb_run_chunk(h, static_cast<const char*>(prev) + b0 * N0 * esz,
                                static_cast<const char*>(next) + b0 * N0 * esz, dtype, H, W, B, *p, layers, pc, ws,
-                               kern_off, flow + b0 * N0 * 2));
+                               kern_off, up_off, flow + b0 * N0 * 2));
     }
     return DATMO_OK;
 }
@@ -1914,7 +1970,13 @@ int datmo_fb_upsample_flow_dev(datmo_handle_t h, const float* flow_in, int h_in,
     DATMO_ENTER(h);
     DATMO_REQUIRE(h, flow_in && flow_out && h_in >= 1 && w_in >= 1 && h_out >= 1 && w_out >= 1 && batch >= 1,
                   "bad arguments");
-    return launch_upsample(h, flow_in, h_in, w_in, flow_out, h_out, w_out, batch, mul);
+    std::vector<float> tab;
+    up_tables(h_in, w_in, h_out, w_out, tab);
+    DATMO_TRY(datmo_ws_reserve(h, tab.size() * sizeof(float) + 256));
+    float* d_tab = reinterpret_cast<float*>(h->ws);
+    DATMO_CHECK_CUDA(h, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));  // tab is a stack-lifetime vector
+    return launch_upsample(h, flow_in, h_in, w_in, flow_out, h_out, w_out, batch, mul, d_tab);
 }
 
 }  // extern "C"
