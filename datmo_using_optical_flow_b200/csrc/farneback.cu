@@ -12,7 +12,7 @@
 //   * the finest layer's pyramid image + polynomial expansion is ONE kernel straight from the
 //     uint8 frame (k_pyr0_polyexp);
 //   * one flow iteration = updateMatrices + 5-channel box blur + 2x2 solve is ONE
-//     kernel (k_flow_iter_w for the reference's window, k_flow_iter otherwise): the M field
+//     kernel (k_flow_iter_xm for the reference's window, k_flow_iter otherwise): the M field
 //     never exists in global memory;
 //   * the 5-coefficient fields R0 / R1 are stored per array of B images as
 //     [B][h*w] float4 (coefficients 0..3) followed by [B][h*w] float (coefficient 4): a
@@ -244,17 +244,6 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
     return i;
-}
-
-// INTER_LINEAR source tap of destination index d (F2): src = (d+0.5)*S/D - 0.5 in
-// fp64 with every operation rounded, then the two clamp rules.
-__device__ __forceinline__ void resize_tap(int d, int S, double ratio, int& s, double& f) {
-    double src = __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(d), 0.5), ratio), -0.5);
-    double fl = floor(src);
-    s = static_cast<int>(fl);
-    f = src - fl;
-    if (s < 0) s = 0, f = 0;
-    if (s >= S - 1) s = S - 1, f = 0;
 }
 
 __device__ __forceinline__ float load_px(const uint8_t* p) { return static_cast<float>(*p); }
@@ -772,7 +761,7 @@ __global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict
 // ------------------------------------------------------------------------------------
 constexpr int FI_TX = 32, FI_TY = 32, FI_THREADS = 256;
 #ifndef DATMO_FI_TILE_DEFAULT
-#define DATMO_FI_TILE_DEFAULT 9
+#define DATMO_FI_TILE_DEFAULT 1
 #endif
 
 __device__ __forceinline__ float2 solve_flow(const float g[5]) {
@@ -926,29 +915,7 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter_w(const float* __restric
             gy = min(max(y0 - M + yy, 0), h - 1);
             so = yy * SW + xx;
         };
-        if (FUSED && MINB >= 3) {
-            // one pixel per trip (fewer live registers -> one more resident CTA); next flow prefetched
-            int gx = 0, gy = 0, so = 0;
-            float2 f = make_float2(0.f, 0.f);
-            int i = tid;
-            if (i < NPIX) {
-                locate(i, gx, gy, so);
-                f = fb[static_cast<size_t>(gy) * w + gx];
-            }
-            for (; i < NPIX; i += NT) {
-                MTaps Ta;
-                m_gather(R0b, R1b, w, h, gx, gy, f, Ta);
-                const int cgx = gx, cgy = gy, cso = so;
-                if (i + NT < NPIX) {
-                    locate(i + NT, gx, gy, so);
-                    f = fb[static_cast<size_t>(gy) * w + gx];
-                }
-                float Mv[5];
-                m_finish(Ta, w, h, cgx, cgy, Mv);
-#pragma unroll
-                for (int c = 0; c < 5; ++c) sM[c * RH * SW + cso] = Mv[c];
-            }
-        } else if (FUSED) {
+        if (FUSED) {
             // 2-D mapping: LW lanes along x, the thread walks the region in (LW, LH) strides, so
             // coordinates are adds; tiles that touch neither the image border nor its 5-px
             // attenuation band (the common case) skip every clamp and the border test.
@@ -1128,13 +1095,13 @@ __device__ __forceinline__ void window_sums_carry(float* v) {
     for (int j = 0; j < WIN - 1; ++j) v[j] = carry[j];
 }
 
-template <int TY_, int NT_, int VSPLIT_, int MINB_, int PIX_, int OPT_ = 0>
+template <int TY_, int NT_, int VSPLIT_, int MINB_, int PIX_>
 struct XmTile {
-    static constexpr int TY = TY_, NT = NT_, VSPLIT = VSPLIT_, MINB = MINB_, PIX = PIX_, OPT = OPT_;
+    static constexpr int TY = TY_, NT = NT_, VSPLIT = VSPLIT_, MINB = MINB_, PIX = PIX_;
     static constexpr int HM = 7, WIN = 15;
     static constexpr int RH = TY + 2 * HM;       // M rows of a group
     static constexpr int MS = 33;                // row stride of the M / G buffer (32 columns + 1)
-    static constexpr int VW = 46, VS = 47;       // vertical-sum window: 14 carried + 32 new columns; odd stride
+    static constexpr int VS = 47;                // vertical-sum window: 14 carried + 32 new columns = 46; odd stride
     static constexpr int M_FLOATS = 5 * RH * MS, V_FLOATS = 5 * TY * VS;
     static constexpr size_t SMEM = static_cast<size_t>(M_FLOATS + V_FLOATS) * sizeof(float);
     static_assert(TY % VSPLIT == 0, "band must split evenly for the vertical pass");
@@ -1257,62 +1224,32 @@ __device__ __forceinline__ void xm_m_phase(float* __restrict__ sM, const float4*
     constexpr int PIX = T::PIX;
     const int r0 = wi * rpw + rsub;
     float* dst = sM + r0 * MS + col;
-    if constexpr ((T::OPT & 2) != 0) {
-        // every trip's flow vectors loaded up front, trips unrolled
-        constexpr int TRIPS = (RH + PIX * NW - 1) / (PIX * NW);  // 32-column groups; the 8-column ones need one
-        float2 f[TRIPS][PIX];
+    // every trip's flow vectors are loaded up front; trips unrolled
+    constexpr int TRIPS = (RH + PIX * NW - 1) / (PIX * NW);  // 32-column groups; the 8-column ones need one
+    float2 f[TRIPS][PIX];
 #pragma unroll
-        for (int t = 0; t < TRIPS; ++t)
-#pragma unroll
-            for (int p = 0; p < PIX; ++p)
-                f[t][p] = __ldg(at_index<8>(fb, min(max(ry0 + r0 + (t * PIX + p) * step, 0), h - 1) * w + gx));
-#pragma unroll
-        for (int t = 0; t < TRIPS; ++t) {
-            const int r = r0 + t * PIX * step;
-            if (r >= RH) break;
-            XmTaps Ta[PIX];
-            int gy[PIX];
-#pragma unroll
-            for (int p = 0; p < PIX; ++p) {
-                gy[p] = min(max(ry0 + r + p * step, 0), h - 1);
-                xm_gather(r0q, r0s, r1q, r1s, w, h, xf, gx, gy[p], f[t][p], Ta[p]);
-            }
-#pragma unroll
-            for (int p = 0; p < PIX; ++p) {
-                float Mv[5];
-                xm_finish(Ta[p], border, w, h, gx, gy[p], Mv);
-                if (p == 0 || r + p * step < RH) {
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) dst[c * RH * MS + (t * PIX + p) * step * MS] = Mv[c];
-                }
-            }
-        }
-    } else {
-        int r = r0;
-        float2 f[PIX];
+    for (int t = 0; t < TRIPS; ++t)
 #pragma unroll
         for (int p = 0; p < PIX; ++p)
-            f[p] = __ldg(at_index<8>(fb, min(max(ry0 + r + p * step, 0), h - 1) * w + gx));
-#pragma unroll 1
-        for (; r < RH; r += PIX * step, dst += PIX * step * MS) {
-            XmTaps Ta[PIX];
-            int gy[PIX];
+            f[t][p] = __ldg(at_index<8>(fb, min(max(ry0 + r0 + (t * PIX + p) * step, 0), h - 1) * w + gx));
 #pragma unroll
-            for (int p = 0; p < PIX; ++p) {
-                gy[p] = min(max(ry0 + r + p * step, 0), h - 1);
-                xm_gather(r0q, r0s, r1q, r1s, w, h, xf, gx, gy[p], f[p], Ta[p]);
-            }
+    for (int t = 0; t < TRIPS; ++t) {
+        const int r = r0 + t * PIX * step;
+        if (r >= RH) break;
+        XmTaps Ta[PIX];
+        int gy[PIX];
 #pragma unroll
-            for (int p = 0; p < PIX; ++p)
-                f[p] = __ldg(at_index<8>(fb, min(max(ry0 + r + (PIX + p) * step, 0), h - 1) * w + gx));
+        for (int p = 0; p < PIX; ++p) {
+            gy[p] = min(max(ry0 + r + p * step, 0), h - 1);
+            xm_gather(r0q, r0s, r1q, r1s, w, h, xf, gx, gy[p], f[t][p], Ta[p]);
+        }
 #pragma unroll
-            for (int p = 0; p < PIX; ++p) {
-                float Mv[5];
-                xm_finish(Ta[p], border, w, h, gx, gy[p], Mv);
-                if (p == 0 || r + p * step < RH) {
+        for (int p = 0; p < PIX; ++p) {
+            float Mv[5];
+            xm_finish(Ta[p], border, w, h, gx, gy[p], Mv);
+            if (p == 0 || r + p * step < RH) {
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) dst[c * RH * MS + p * step * MS] = Mv[c];
-                }
+                for (int c = 0; c < 5; ++c) dst[c * RH * MS + (t * PIX + p) * step * MS] = Mv[c];
             }
         }
     }
@@ -1562,29 +1499,13 @@ int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float
     int m = winsize / 2;
     float norm = static_cast<float>(1.0 / (static_cast<double>(winsize) * winsize));
     if (m == 7 && !getenv("DATMO_GENERIC_FLOW_ITER")) {
-        // the reference's winsize 15 (and 14): compile-time window.  DATMO_FI_TILE selects the A/B
-        // alternatives measured in DESIGN.md §5 (1: 32x32 tile, one pixel per trip, 4 CTAs/SM;
-        // 2: 64x64 tile, 512 threads, 1 CTA/SM); all three land within 3 % of each other
+        // the reference's winsize 15 (and 14): compile-time window.  The fused iteration runs the
+        // x-marching kernel; DATMO_FI_TILE=0 selects the 64x32 tile kernel it replaced (A/B runs,
+        // DESIGN.md §5), which also serves the blur-and-solve-only entry point.
         static const int tile = flow_tile_choice();
-        if (FUSED) {
-            switch (tile) {
-                case 3: return launch_flow_iter_xm<XmTile<64, 320, 2, 2, 1>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                case 4: return launch_flow_iter_xm<XmTile<48, 320, 2, 2, 1>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                case 5: return launch_flow_iter_xm<XmTile<32, 160, 1, 3, 1>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                case 6: return launch_flow_iter_xm<XmTile<64, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                case 7: return launch_flow_iter_xm<XmTile<32, 160, 1, 3, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                case 8: return launch_flow_iter_xm<XmTile<48, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                case 9: return launch_flow_iter_xm<XmTile<46, 320, 2, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                case 10: return launch_flow_iter_xm<XmTile<26, 320, 1, 3, 1>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                case 12: return launch_flow_iter_xm<XmTile<46, 320, 2, 2, 2, 0>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
-                default: break;
-            }
-        }
-        switch (tile) {
-            case 1: return launch_flow_iter_w<32, 32, 256, 4, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            case 2: return launch_flow_iter_w<64, 64, 512, 1, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-            default: return launch_flow_iter_w<64, 32, 256, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
-        }
+        if (FUSED && tile != 0)
+            return launch_flow_iter_xm<XmTile<46, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+        return launch_flow_iter_w<64, 32, 256, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
     }
     size_t smem = flow_iter_smem(m);
     DATMO_REQUIRE(h, smem <= 227 * 1024, "winsize too large for the flow-iteration tile");
