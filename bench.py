@@ -50,6 +50,17 @@ def algorithmic_bytes(H, W, fb=FB):
     return A, iters * 56 * sumN, len(layers)
 
 
+def ncu_traffic():
+    """DRAM bytes of the dominant kernel's launch from the committed `ncu --set full` capture
+    (profiles/roofline_traffic.json, written by tools/ncu_summary.py --traffic); None if absent."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)
+    except (OSError, ValueError):
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -59,8 +70,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up until after the
+    timed region; stop() keeps the samples whose timestamps fall inside the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -68,26 +80,35 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"],
+                                          "-i", str(self.index), "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         with open(self.path) as fh:
             for line in fh:
@@ -95,18 +116,22 @@ class ClockSampler:
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for name, val in zip(names, f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
         os.unlink(self.path)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        window = "timed region"
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        if not inside:
+            # a timed region shorter than the sampling period: the samples of the whole loaded run
+            # (warm-up, timed steps, end-to-end leg) stand in
+            inside, window = rows, "whole run (timed region shorter than the sampling period)"
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+                "reasons": reasons, "samples": len(inside), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -244,18 +269,19 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ---------------------------------------------------------------
-    for i in range(args.warmup):
-        res = step(i)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        res = step(i)
+    barrier()
     for e in engines:
         e.profile(True)
         e.profile_reset()
     launches0 = sum(e.launch_count() for e in engines)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     main_stream = torch.cuda.current_stream()
+    sampler.mark_begin()
     ev0.record(main_stream)
     for e in engines:
         e.stream.wait_event(ev0)
@@ -265,6 +291,7 @@ def run_ours(args):
         main_stream.wait_stream(e.stream)
     ev1.record(main_stream)
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = sum(e.launch_count() for e in engines) - launches0
     prof = None
@@ -277,7 +304,6 @@ def run_ours(args):
             for k in prof:
                 prof[k]["ms"] += p[k]["ms"]
                 prof[k]["launches"] += p[k]["launches"]
-    clocks = sampler.stop() if rank == 0 else None
     n_valid_mean = float(res.n_valid.float().mean().item())
     n_clusters_mean = float(res.n_clusters.float().mean().item())
     truncated = bool((res.n_valid > args.cap).any().item())
@@ -333,9 +359,11 @@ def run_ours(args):
     else:
         shard_stats = shard.cpu().numpy()[None]
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         A, iter_bytes, n_layers = algorithmic_bytes(H, W)
         peak, peak_src = measured_peaks()
+        traffic = ncu_traffic()
         it = prof["flow_iter"]
         it_ms = it["ms"] / max(it["launches"], 1)
         # algorithmic bytes of the flow-iteration launches of one step / their summed device time
@@ -353,9 +381,11 @@ def run_ours(args):
                             "cluster summaries, every step; copies double-buffered against compute; wall clock"},
             "gpu_launches": int(lc.item()),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_flow_iter<fused> (updateMatrices + box blur + solve)",
+            "roofline": {"bound": "hbm", "kernel": "k_flow_iter_xm (updateMatrices + 15x15 box sums + 2x2 solve, fused)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src,
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_capture": traffic,
                          "bytes_per_launch_model": "56 B x layer pixels x pairs (R0 20 + R1 20 + flow 8 in, flow 8 out)",
                          "avg_launch_ms": it_ms, "launches": it["launches"],
                          "whole_pipeline": {"A_bytes_per_pair": A, "achieved_gbs_per_gpu": whole,
@@ -384,7 +414,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--size", type=int, default=1024)

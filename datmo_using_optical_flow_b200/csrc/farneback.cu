@@ -1178,15 +1178,16 @@ __device__ __forceinline__ void xm_finish(const XmTaps& T, bool border, int w, i
 
 // L2 prefetch of everything the NEXT group's M phase will read (R0, R1 at zero displacement, flow):
 // a group's columns are new to the whole GPU, so without this every gather of the M phase waits on
-// DRAM; with it they wait on L2.  One 128-byte line per instruction, 12 lines per row.
+// DRAM; with it they wait on L2.  One 128-byte line per instruction, 12 lines per row; the row
+// index runs fastest so a warp works on one kind of line (cp.async.bulk.prefetch was measured
+// slower than no prefetch at all for these 128..512-byte runs).
 template <typename T>
 __device__ __forceinline__ void xm_prefetch(const float4* r0q, const float* r0s, const float4* r1q,
                                             const float* r1s, const float2* fb, int w, int h, int cx, int ry0) {
     if (cx >= w) return;
     for (int i = threadIdx.x; i < T::RH * 12; i += T::NT) {
-        const int row = i / 12, j = i - row * 12;
-        const int gy = min(max(ry0 + row, 0), h - 1);
-        const int o = gy * w + cx;
+        const int j = i / T::RH, row = i - j * T::RH;
+        const int o = min(max(ry0 + row, 0), h - 1) * w + cx;
         const char* p;
         if (j < 4)
             p = reinterpret_cast<const char*>(r0q + o) + j * 128;
@@ -1276,6 +1277,8 @@ __device__ __forceinline__ void xm_h_phase(float* sV) {
     for (int i = threadIdx.x; i < 5 * T::TY; i += T::NT) window_sums_carry<T::WIN, 32>(sV + i * T::VS);  // i = c * TY + row
 }
 
+// 2x2 solve on the raw window sums: norm^2 scales the determinant and both numerators alike
+// (the regulariser 1e-3 belongs to the normalised determinant, as in solve_flow)
 template <typename T>
 __device__ __forceinline__ void xm_solve(const float* sV, float2* __restrict__ fo, int w, int h, int y0, int c0,
                                          int xlo, int xhi, float norm) {
@@ -1283,13 +1286,14 @@ __device__ __forceinline__ void xm_solve(const float* sV, float2* __restrict__ f
     const int gx = c0 - T::HM + lane;
     if (gx < xlo || gx >= xhi) return;
     const int rows = min(T::TY, h - y0);
+    const float n2 = norm * norm;
     float2* out = fo + static_cast<size_t>(y0 + wi) * w + gx;
     const float* g = sV + wi * T::VS + (T::WIN - 1) + lane;
     for (int row = wi; row < rows; row += T::NT / 32, out += (T::NT / 32) * w, g += (T::NT / 32) * T::VS) {
-        float v[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) v[c] = g[c * T::TY * T::VS] * norm;
-        *out = solve_flow(v);
+        const float g0 = g[0], g1 = g[T::TY * T::VS], g2 = g[2 * T::TY * T::VS], g3 = g[3 * T::TY * T::VS],
+                    g4 = g[4 * T::TY * T::VS];
+        const float t = n2 * __fdividef(1.f, fmaf(g0 * g2 - g1 * g1, n2, 1e-3f));
+        *out = make_float2((g0 * g4 - g1 * g3) * t, (g2 * g3 - g1 * g4) * t);
     }
 }
 

@@ -9,6 +9,7 @@ utilisation, occupancy limiters and the top warp-stall reasons.
 """
 import csv
 import io
+import os
 import subprocess
 import sys
 
@@ -43,7 +44,28 @@ KEYS = [
 ]
 
 
+def traffic_json(rep: str, note: str) -> None:
+    """`--traffic NOTE`: DRAM read + write bytes of the first captured launch as JSON (bench.py's roofline.traffic)."""
+    import json
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    head, units, first = rows[0], rows[1], rows[2]
+    d, u = dict(zip(head, first)), dict(zip(head, units))
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def nbytes(k):
+        return float(d[k].replace(",", "")) * scale[u[k]]
+    t_us = float(d["gpu__time_duration.sum"].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3}[u["gpu__time_duration.sum"]]
+    print(json.dumps({"kernel": d["Kernel Name"].split("(")[0], "grid": d["Grid Size"], "block": d["Block Size"],
+                      "dram_bytes_per_launch": nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum"),
+                      "dram_read_bytes": nbytes("dram__bytes_read.sum"), "dram_write_bytes": nbytes("dram__bytes_write.sum"),
+                      "duration_us_under_ncu": t_us, "capture": os.path.basename(rep), "launch": note}, indent=1))
+
+
 def main() -> None:
+    if len(sys.argv) > 3 and sys.argv[2] == "--traffic":
+        traffic_json(sys.argv[1], sys.argv[3])
+        return
     rep = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
