@@ -55,6 +55,7 @@ SIGNATURES = {
     "datmo_synchronize": (_i, [_vp]),
     "datmo_workspace_bytes": (C.c_size_t, [_vp]),
     "datmo_profile_enable": (_i, [_vp, _i]),
+    "datmo_profile_tags": (_i, [_vp, C.c_uint]),
     "datmo_profile_reset": (_i, [_vp]),
     "datmo_profile_read": (_i, [_vp, C.POINTER(_i64), C.POINTER(_d)]),
     "datmo_launch_count": (_i64, [_vp]),

@@ -24,8 +24,14 @@ struct datmo_ctx {
     char* pinned = nullptr;
     size_t pinned_cap = 0;
     std::string err;
+    // Farneback per-layer tables (pyramid taps, upsampling taps): cached on the device across calls
+    // with the same geometry, so a steady-state call uploads nothing and never blocks the host
+    float* fb_tab = nullptr;
+    size_t fb_tab_cap = 0;          // floats
+    std::vector<float> fb_tab_host;  // what fb_tab holds
     // profiling
     bool prof = false;
+    unsigned prof_mask = 0xffffffffu;  // tags that get event pairs while prof is on
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     std::vector<std::pair<int, int>> ev_used;  // (tag, pool index)
     int64_t prof_launches[DATMO_TAG_COUNT] = {0};

@@ -27,7 +27,7 @@ int datmo_pinned_reserve(datmo_ctx* h, size_t bytes) {
 
 LaunchScope::LaunchScope(datmo_ctx* h_, int tag, int n_launches) : h(h_) {
     h->launches += n_launches;
-    if (!h->prof) return;
+    if (!h->prof || !((h->prof_mask >> tag) & 1u)) return;
     h->prof_launches[tag] += n_launches;
     size_t used = h->ev_used.size();
     if (used >= h->ev_pool.size()) {
@@ -98,6 +98,7 @@ int datmo_destroy(datmo_handle_t h) {
         cudaEventDestroy(ev.second);
     }
     if (h->ws) cudaFree(h->ws);
+    if (h->fb_tab) cudaFree(h->fb_tab);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -114,10 +115,13 @@ int datmo_synchronize(datmo_handle_t h) {
 
 size_t datmo_workspace_bytes(datmo_handle_t h) { return h ? h->ws_cap : 0; }
 
-int datmo_profile_enable(datmo_handle_t h, int on) {
+int datmo_profile_enable(datmo_handle_t h, int on) { return datmo_profile_tags(h, on ? 0xffffffffu : 0u); }
+
+int datmo_profile_tags(datmo_handle_t h, unsigned mask) {
     if (!h) return DATMO_E_INVALID;
     DATMO_TRY(profile_drain(h));
-    h->prof = on != 0;
+    h->prof = mask != 0;
+    h->prof_mask = mask;
     return DATMO_OK;
 }
 

@@ -1626,7 +1626,8 @@ struct FbWorkspace {
 
 size_t fb_carve(Bump& bump, FbWorkspace& ws, int H, int W, int B, int n_kern, bool need_M) {
     size_t N0 = static_cast<size_t>(H) * W;
-    ws.kern = bump.take<float>(n_kern);
+    (void)n_kern;  // the tables live outside the arena (datmo_ctx::fb_tab)
+    ws.kern = nullptr;
     ws.T = bump.take<float>(B * N0);
     ws.I = bump.take<float>(2 * B * N0);
     ws.R = bump.take<float>(2 * r_array_stride(B, N0));
@@ -1733,12 +1734,23 @@ int fb_run(datmo_ctx* h, const void* prev, const void* next, int dtype, int H, i
     DATMO_TRY(datmo_ws_reserve(h, total));
     Bump bump(h->ws);
     fb_carve(bump, ws, H, W, chunk, static_cast<int>(kern_all.size()), need_M);
-    // taps go through the pinned staging area so the copy is truly asynchronous
-    DATMO_TRY(datmo_pinned_reserve(h, kern_all.size() * sizeof(float)));
-    DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));  // previous call may still read the staging area
-    memcpy(h->pinned, kern_all.data(), kern_all.size() * sizeof(float));
-    DATMO_CHECK_CUDA(h, cudaMemcpyAsync(ws.kern, h->pinned, kern_all.size() * sizeof(float), cudaMemcpyHostToDevice,
-                                        h->stream));
+    // the tables live in their own device buffer and are uploaded only when the geometry changes
+    if (h->fb_tab_host != kern_all) {
+        DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));  // an earlier call may still read the old tables
+        if (kern_all.size() > h->fb_tab_cap) {
+            if (h->fb_tab) DATMO_CHECK_CUDA(h, cudaFree(h->fb_tab));
+            h->fb_tab = nullptr;
+            h->fb_tab_cap = 0;
+            h->fb_tab_host.clear();
+            DATMO_CHECK_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->fb_tab), kern_all.size() * sizeof(float)));
+            h->fb_tab_cap = kern_all.size();
+        }
+        DATMO_CHECK_CUDA(h, cudaMemcpyAsync(h->fb_tab, kern_all.data(), kern_all.size() * sizeof(float),
+                                            cudaMemcpyHostToDevice, h->stream));
+        DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));  // kern_all is a stack-lifetime vector
+        h->fb_tab_host = kern_all;
+    }
+    ws.kern = h->fb_tab;
     const size_t N0 = static_cast<size_t>(H) * W;
     const size_t esz = dtype == DATMO_U8 ? 1 : 4;
     for (int b0 = 0; b0 < batch; b0 += chunk) {

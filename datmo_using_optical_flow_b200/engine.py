@@ -108,8 +108,15 @@ class Engine:
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.tdev)
 
-    def profile(self, on: bool):
-        self._check(self.lib.datmo_profile_enable(self.h, int(on)))
+    def profile(self, on: bool, tags=None):
+        """Bracket tagged launches with CUDA events; `tags` (names from _lib.TAGS) restricts it to those."""
+        if on and tags is not None:
+            mask = 0
+            for t in tags:
+                mask |= 1 << _lib.TAGS.index(t)
+            self._check(self.lib.datmo_profile_tags(self.h, mask))
+        else:
+            self._check(self.lib.datmo_profile_enable(self.h, int(on)))
 
     def profile_reset(self):
         self._check(self.lib.datmo_profile_reset(self.h))

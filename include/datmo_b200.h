@@ -75,6 +75,9 @@ size_t datmo_workspace_bytes(datmo_handle_t h);
 #define DATMO_TAG_CLUSTER 8
 #define DATMO_TAG_COUNT 9
 int datmo_profile_enable(datmo_handle_t h, int on);
+/* time only the tags whose bit (1u << DATMO_TAG_x) is set in mask (0 = off): the event pairs cost
+ * a few microseconds per launch, so a benchmark brackets just the kernel it reports on */
+int datmo_profile_tags(datmo_handle_t h, unsigned mask);
 int datmo_profile_reset(datmo_handle_t h);
 int datmo_profile_read(datmo_handle_t h, int64_t launches[DATMO_TAG_COUNT], double ms[DATMO_TAG_COUNT]);
 /* total kernel launches issued by this handle since creation */
