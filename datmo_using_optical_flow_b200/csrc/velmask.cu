@@ -120,7 +120,106 @@ __global__ void __launch_bounds__(256) k_curl_filtered(const float* __restrict__
     ang_f[base + o] = static_cast<float>(dvy_dx - dvx_dy);
 }
 
+// ---- propagation masks (main.py:166-221) ---------------------------------------------------------
+// The reference scatters every cell's velocity to the cell it would reach after dt, in row-major
+// order, so the LAST source wins a contested target; then compares the scattered field with the
+// actual one.  Here: atomicMax of the source rank per target, then a gather.  T is the dtype the
+// reference would compute in (f32 for the velocities of compute_velocity_vectors, f64 otherwise);
+// every operation is rounded separately, in numpy's order.
+template <typename T>
+struct PropOps;
+template <>
+struct PropOps<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <>
+struct PropOps<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_prop_scatter(const T* __restrict__ vx, const T* __restrict__ vy,
+                                                      const T* __restrict__ ax, const T* __restrict__ ay, int H,
+                                                      int W, T dt, T dt2, T gx, T gy, int32_t* __restrict__ winner) {
+    using O = PropOps<T>;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y, b = blockIdx.z;
+    if (j >= W) return;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const int o = i * W + j;
+    T sx = O::mul(vx[base + o], dt), sy = O::mul(vy[base + o], dt);
+    if (ax) {
+        sx = O::add(sx, O::mul(O::mul(static_cast<T>(0.5), ax[base + o]), dt2));
+        sy = O::add(sy, O::mul(O::mul(static_cast<T>(0.5), ay[base + o]), dt2));
+    }
+    const T ti = O::add(static_cast<T>(i), floor(O::div(sx, gx)));
+    const T tj = O::add(static_cast<T>(j), floor(O::div(sy, gy)));
+    // int() truncates; NaN / inf (the reference raises on them) and out-of-grid targets do not propagate
+    if (!(ti > static_cast<T>(-1) && ti < static_cast<T>(H) && tj > static_cast<T>(-1) && tj < static_cast<T>(W))) return;
+    const int ii = static_cast<int>(ti), jj = static_cast<int>(tj);
+    if (ii < 0 || jj < 0) return;  // (-1, 0) truncates to 0 and IS a hit; below -1 never gets here
+    atomicMax(winner + base + static_cast<size_t>(ii) * W + jj, o);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_prop_mask(const T* __restrict__ vx, const T* __restrict__ vy, int H, int W,
+                                                   T alpha, const int32_t* __restrict__ winner,
+                                                   uint8_t* __restrict__ mask) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y, b = blockIdx.z;
+    if (j >= W) return;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const size_t o = base + static_cast<size_t>(i) * W + j;
+    const int wn = winner[o];
+    const T pvx = wn >= 0 ? vx[base + wn] : static_cast<T>(0), pvy = wn >= 0 ? vy[base + wn] : static_cast<T>(0);
+    mask[o] = (fabs(pvx - vx[o]) <= alpha) && (fabs(pvy - vy[o]) <= alpha);
+}
+
+template <typename T>
+int prop_run(datmo_ctx* h, const T* vx, const T* vy, const T* ax, const T* ay, int H, int W, int batch, double dt,
+             double gx, double gy, double alpha_p, uint8_t* mask) {
+    const size_t n = static_cast<size_t>(batch) * H * W;
+    DATMO_TRY(datmo_ws_reserve(h, n * sizeof(int32_t) + 256));
+    int32_t* winner = reinterpret_cast<int32_t*>(h->ws);
+    DATMO_CHECK_CUDA(h, cudaMemsetAsync(winner, 0xff, n * sizeof(int32_t), h->stream));
+    dim3 g(ceil_div(W, 256), H, batch);
+    {
+        LaunchScope ls(h, DATMO_TAG_VELMASK);
+        k_prop_scatter<T><<<g, 256, 0, h->stream>>>(vx, vy, ax, ay, H, W, static_cast<T>(dt), static_cast<T>(dt * dt),
+                                                    static_cast<T>(gx), static_cast<T>(gy), winner);
+    }
+    DATMO_POST_LAUNCH(h);
+    {
+        LaunchScope ls(h, DATMO_TAG_VELMASK);
+        k_prop_mask<T><<<g, 256, 0, h->stream>>>(vx, vy, H, W, static_cast<T>(alpha_p), winner, mask);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
 }  // namespace
+
+extern "C" int datmo_propagation_mask_dev(datmo_handle_t h, const void* vx, const void* vy, const void* ax,
+                                          const void* ay, int dtype, int H, int W, int batch, double dt, double grid_x,
+                                          double grid_y, double alpha_p, uint8_t* mask) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, vx && vy && mask && H >= 1 && W >= 1 && batch >= 1, "bad arguments");
+    DATMO_REQUIRE(h, (ax == nullptr) == (ay == nullptr), "ax and ay come together");
+    DATMO_REQUIRE(h, dtype == DATMO_F32 || dtype == DATMO_F64, "dtype must be DATMO_F32 or DATMO_F64");
+    DATMO_REQUIRE(h, static_cast<int64_t>(H) * W < (int64_t(1) << 31), "grid too large for int32 cell indices");
+    DATMO_REQUIRE(h, H <= 65535 && batch <= 65535, "H and batch must fit a CUDA grid dimension");
+    if (dtype == DATMO_F32)
+        return prop_run<float>(h, static_cast<const float*>(vx), static_cast<const float*>(vy),
+                               static_cast<const float*>(ax), static_cast<const float*>(ay), H, W, batch, dt, grid_x,
+                               grid_y, alpha_p, mask);
+    return prop_run<double>(h, static_cast<const double*>(vx), static_cast<const double*>(vy),
+                            static_cast<const double*>(ax), static_cast<const double*>(ay), H, W, batch, dt, grid_x,
+                            grid_y, alpha_p, mask);
+}
 
 extern "C" int datmo_velocity_mask_dev(datmo_handle_t h, const float* flow, int H, int W, int batch, double px_x,
                                        double px_y, double alpha_cont, double thresh, float* vx, float* vy, float* ang,

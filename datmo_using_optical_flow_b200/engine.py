@@ -246,6 +246,21 @@ class Engine:
                 _ptr(out["vy_f"]), _ptr(out["ang_f"]), _ptr(out["valid"]), _ptr(out["n_valid"])))
         return {k: v for k, v in out.items() if v is not None}
 
+    def propagation_mask(self, vx: torch.Tensor, vy: torch.Tensor, dt: float, grid_resolution, alpha_p: float,
+                         ax: torch.Tensor | None = None, ay: torch.Tensor | None = None) -> torch.Tensor:
+        """[B,H,W] (or [H,W]) f32 / f64 velocities (and accelerations) -> uint8 mask, see datmo_propagation_mask_dev."""
+        with self.on_stream():
+            squeeze = vx.dim() == 2
+            ts = [t if t is None else (t.unsqueeze(0) if squeeze else t) for t in (vx, vy, ax, ay)]
+            dtype = torch.float64 if vx.dtype == torch.float64 else torch.float32
+            ts = [t if t is None else t.to(dtype).contiguous() for t in ts]
+            B, H, W = ts[0].shape
+            mask = self.empty((B, H, W), torch.uint8)
+            self._check(self.lib.datmo_propagation_mask_dev(
+                self.h, _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]), 2 if dtype == torch.float64 else 1, H, W, B,
+                float(dt), float(grid_resolution[0]), float(grid_resolution[1]), float(alpha_p), _ptr(mask)))
+        return mask[0] if squeeze else mask
+
     # -- DBSCAN ---------------------------------------------------------------------------------
     def dbscan_grid(self, vx_f, vy_f, valid, eps: float, min_samples: int, cap: int | None = None):
         """-> (n_valid [B] i32, labels [B,cap] i32, indices [B,cap,2] i32, n_clusters [B] i32), device."""

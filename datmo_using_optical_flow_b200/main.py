@@ -22,7 +22,8 @@ from . import _lib
 from .engine import Engine, default_engine, farneback_params
 
 __all__ = ["filter_points_in_roi", "increase_point_density", "compute_bev_grid", "preprocess_points",
-           "preprocess_pcd", "compute_velocity_vectors", "continuity_mask", "moving_cell_filter",
+           "preprocess_pcd", "compute_velocity_vectors", "continuity_mask", "propagation_mask",
+           "propagation_mask_with_acceleration", "moving_cell_filter",
            "dbscan_clustering", "extract_cluster_data", "flow_to_clusters", "read_pcd"]
 
 
@@ -214,6 +215,30 @@ def continuity_mask(vx, vy, alpha_cont, engine=None):
         eng.synchronize()
         return m.cpu().numpy().astype(np.int64)
     return m.to(torch.int64)
+
+
+def _propagation(vx, vy, ax, ay, dt, grid_resolution, alpha_p, engine):
+    eng = engine or default_engine()
+    as_np = _is_np(vx, vy)
+    # the reference computes in the dtype of its inputs: f32 velocities stay f32, anything else is f64
+    dtype = torch.float32 if (getattr(vx, "dtype", None) in (np.float32, torch.float32)) else torch.float64
+    dev = [None if t is None else _to_dev(eng, t, dtype) for t in (vx, vy, ax, ay)]
+    m = eng.propagation_mask(dev[0], dev[1], dt, grid_resolution, alpha_p, dev[2], dev[3])
+    if as_np:
+        eng.synchronize()
+        return m.cpu().numpy().astype(np.int64)
+    return m.to(torch.int64)
+
+
+def propagation_mask(vx, vy, dt, grid_resolution, alpha_p, engine=None):
+    """main.py:166-182 -> int64 0/1 (H,W): forward scatter of every cell's velocity (last source in
+    row-major order wins), compared with the actual field."""
+    return _propagation(vx, vy, None, None, dt, grid_resolution, alpha_p, engine)
+
+
+def propagation_mask_with_acceleration(vx, vy, ax, ay, dt, grid_resolution, alpha_p, engine=None):
+    """main.py:184-221: the same with the displacement (v dt + a dt^2 / 2)."""
+    return _propagation(vx, vy, ax, ay, dt, grid_resolution, alpha_p, engine)
 
 
 def moving_cell_filter(vx, vy, alpha_cont, thresh=0.1, engine=None):

@@ -44,6 +44,7 @@ typedef struct datmo_ctx* datmo_handle_t;
 /* image element types for the Farneback inputs */
 #define DATMO_U8 0
 #define DATMO_F32 1
+#define DATMO_F64 2   /* propagation masks only */
 /* point layouts */
 #define DATMO_PTS_F64_XYZ 0  /* double[n][3], what main.py passes around */
 #define DATMO_PTS_F32_XYZW 1 /* float[n][4], CARLA's native layout */
@@ -140,6 +141,21 @@ int datmo_velocity_mask_dev(datmo_handle_t h, const float* flow, int H, int W, i
                             double px_y, double alpha_cont, double thresh, float* vx, float* vy,
                             float* ang, uint8_t* mask, float* vx_f, float* vy_f, float* ang_f,
                             uint8_t* valid, int32_t* n_valid);
+
+/* ---- propagation masks ---------------------------------------------------------
+ * Replaces propagation_mask (main.py:166-182) and propagation_mask_with_acceleration
+ * (main.py:184-221; pass ax = ay = NULL for the former).  The reference defines both
+ * and its driver never calls them (main.py:596-597 is commented out); they are here
+ * because its README lists them as part of the method.
+ * vx, vy (ax, ay): [batch][H][W] of dtype DATMO_F32 or DATMO_F64 — the dtype the
+ * reference would compute in.  Every cell's velocity is scattered to
+ * (i + floor(vx dt / grid_x), j + floor(vy dt / grid_y)); among several sources of one
+ * target the LAST in row-major order wins (the reference's double loop); mask =
+ * |scattered - actual| <= alpha_p on both components, uint8 0/1 [batch][H][W].
+ * NaN / inf displacements (the reference raises on them) do not propagate. */
+int datmo_propagation_mask_dev(datmo_handle_t h, const void* vx, const void* vy, const void* ax,
+                               const void* ay, int dtype, int H, int W, int batch, double dt,
+                               double grid_x, double grid_y, double alpha_p, uint8_t* mask);
 
 /* ---- DBSCAN over (row, col, vx, vy) of the valid cells --------------------------
  * Replaces dbscan_clustering, main.py:231-259 (sklearn.cluster.DBSCAN on the

@@ -60,3 +60,48 @@ def moving_cell_filter(vx: np.ndarray, vy: np.ndarray, mask: np.ndarray, thresh:
     mag = np.sqrt(vx_f ** 2 + vy_f ** 2)
     ang = gradient(vy_f, 1) - gradient(vx_f, 0)
     return vx_f, vy_f, mag, ang, mag > thresh
+
+
+def _propagate(vx, vy, di, dj, alpha_p):
+    """Forward scatter with last-writer-wins in row-major order (the reference's double loop,
+    main.py:172-178 / 209-216), vectorised: the winner of a target cell is the LARGEST source
+    rank that lands on it."""
+    h, w = vx.shape
+    i, j = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    # `i + np.floor(...)`: python int + np.float32 stays float32 (NEP 50); int() truncates
+    with np.errstate(invalid="ignore", over="ignore"):
+        ti = (i.astype(vx.dtype) + di)
+        tj = (j.astype(vx.dtype) + dj)
+    ok = np.isfinite(ti) & np.isfinite(tj)
+    ti_i = np.where(ok, np.trunc(np.where(ok, ti, 0)), -1).astype(np.int64)
+    tj_i = np.where(ok, np.trunc(np.where(ok, tj, 0)), -1).astype(np.int64)
+    ok &= (ti_i >= 0) & (ti_i < h) & (tj_i >= 0) & (tj_i < w)
+    rank = (i * w + j)[ok]
+    target = (ti_i * w + tj_i)[ok]
+    winner = np.full(h * w, -1, np.int64)
+    np.maximum.at(winner, target, rank)
+    pvx = np.zeros(h * w, vx.dtype)
+    pvy = np.zeros(h * w, vy.dtype)
+    hit = winner >= 0
+    pvx[hit] = vx.ravel()[winner[hit]]
+    pvy[hit] = vy.ravel()[winner[hit]]
+    pvx, pvy = pvx.reshape(h, w), pvy.reshape(h, w)
+    return ((np.abs(pvx - vx) <= alpha_p) & (np.abs(pvy - vy) <= alpha_p)).astype(np.int64)
+
+
+def propagation_mask(vx, vy, dt, grid_resolution, alpha_p):
+    """main.py:166-182 (defined by the reference, never called by its driver).  NaN / inf
+    displacements make the reference's int() raise; here they simply do not propagate."""
+    with np.errstate(invalid="ignore", over="ignore"):
+        di = np.floor(vx * dt / grid_resolution[0])
+        dj = np.floor(vy * dt / grid_resolution[1])
+    return _propagate(vx, vy, di, dj, alpha_p)
+
+
+def propagation_mask_with_acceleration(vx, vy, ax, ay, dt, grid_resolution, alpha_p):
+    """main.py:184-221."""
+    dx, dy = grid_resolution
+    with np.errstate(invalid="ignore", over="ignore"):
+        di = np.floor((vx * dt + 0.5 * ax * dt ** 2) / dx)
+        dj = np.floor((vy * dt + 0.5 * ay * dt ** 2) / dy)
+    return _propagate(vx, vy, di, dj, alpha_p)

@@ -128,6 +128,41 @@ def main():
 
 
 
+def propagation_golden():
+    """propagation_mask / propagation_mask_with_acceleration (main.py:166-221) — the reference's own
+    double loops — on small seeded fields: f32 velocities as compute_velocity_vectors returns them,
+    an f64 case, collisions (several sources per target), sources that leave the grid."""
+    ref = ref_loader.load_reference_main()
+    rng = np.random.default_rng(31)
+    out = {"versions": versions()}
+    cases = []
+    for k, (h, w, scale, dt, gr, alpha, dtype) in enumerate([
+            (40, 56, 0.6, 1.0, (0.25, 0.25), 0.2, np.float32),
+            (33, 47, 3.0, 0.5, (0.25, 0.2), 0.5, np.float32),
+            (25, 31, 9.0, 0.1, (0.125, 0.125), 1.0, np.float32),
+            (21, 18, 2.0, 1.0, (0.25, 0.25), 0.3, np.float64)]):
+        # piecewise-constant blobs (targets collide) + noise
+        vx = np.zeros((h, w))
+        vy = np.zeros((h, w))
+        for _ in range(6):
+            y, x = rng.integers(0, h - 6), rng.integers(0, w - 6)
+            vx[y:y + 6, x:x + 6] = rng.normal() * scale
+            vy[y:y + 6, x:x + 6] = rng.normal() * scale
+        vx = (vx + rng.normal(scale=0.05 * scale, size=(h, w))).astype(dtype)
+        vy = (vy + rng.normal(scale=0.05 * scale, size=(h, w))).astype(dtype)
+        ax = rng.normal(scale=scale, size=(h, w)).astype(dtype)
+        ay = rng.normal(scale=scale, size=(h, w)).astype(dtype)
+        out[f"vx_{k}"], out[f"vy_{k}"], out[f"ax_{k}"], out[f"ay_{k}"] = vx, vy, ax, ay
+        out[f"params_{k}"] = np.array([dt, gr[0], gr[1], alpha])
+        out[f"mask_{k}"] = ref.propagation_mask(vx, vy, dt, list(gr), alpha)
+        out[f"mask_acc_{k}"] = ref.propagation_mask_with_acceleration(vx, vy, ax, ay, dt, list(gr), alpha)
+        cases.append(k)
+    out["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(OUT, "propagation.npz"), **out)
+    print("propagation.npz", os.path.getsize(os.path.join(OUT, "propagation.npz")), "bytes",
+          [float(out[f"mask_{k}"].mean()) for k in cases])
+
+
 def tracker_golden():
     """Reference EKF / track_clusters / manage_tracks + the driver's lifetime bookkeeping
     (main.py:437-515, 618-634) on a seeded stream of cluster dictionaries."""
@@ -171,6 +206,10 @@ def tracker_golden():
 
 
 if __name__ == "__main__":
-    if "--tracks-only" not in sys.argv:
-        main()
-    tracker_golden()
+    if "--propagation-only" in sys.argv:
+        propagation_golden()
+    else:
+        if "--tracks-only" not in sys.argv:
+            main()
+            propagation_golden()
+        tracker_golden()

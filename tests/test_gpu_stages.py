@@ -84,6 +84,33 @@ def test_velocity_and_masks_exact(engine, golden):
         assert int(host(vm["n_valid"])[b]) == int(valid.sum())
 
 
+@pytest.mark.parametrize("k", range(4))
+def test_propagation_masks_exact(engine, golden, k):
+    """main.py:166-221 through the C ABI: identical to the reference's double loops (golden) and, on a
+    1024^2 field, to the oracle; f32 and f64 inputs keep the reference's dtype semantics."""
+    g = golden("propagation.npz")
+    dt, gx, gy, alpha = (float(v) for v in g[f"params_{k}"])
+    vx, vy, ax, ay = (g[f"{n}_{k}"] for n in ("vx", "vy", "ax", "ay"))
+    m = main.propagation_mask(vx, vy, dt, [gx, gy], alpha, engine=engine)
+    assert m.dtype == np.int64 and np.array_equal(m, g[f"mask_{k}"])
+    m = main.propagation_mask_with_acceleration(vx, vy, ax, ay, dt, [gx, gy], alpha, engine=engine)
+    assert np.array_equal(m, g[f"mask_acc_{k}"])
+
+
+def test_propagation_mask_large_batched(engine):
+    rng = np.random.default_rng(9)
+    B, H, W = 3, 1024, 1024
+    vx = (rng.normal(size=(B, H, W)) * 1.5).astype(np.float32)
+    vy = (rng.normal(size=(B, H, W)) * 1.5).astype(np.float32)
+    vx[:, 100:400, 200:700] = 0.8          # a coherent mover: many sources per target band
+    vy[:, 100:400, 200:700] = -0.45
+    vx[0, 5, 5], vy[0, 6, 6] = np.nan, np.inf    # the reference raises on these; here they do not propagate
+    got = host(engine.propagation_mask(dev(vx), dev(vy), 1.0, [0.1, 0.1], 0.2))
+    for b in range(B):
+        want = masks_np.propagation_mask(vx[b], vy[b], 1.0, [0.1, 0.1], 0.2)
+        assert np.array_equal(got[b].astype(np.int64), want)
+
+
 # ---- DBSCAN ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("i", range(5))
 def test_dbscan_golden_labels_identical(engine, golden, i):

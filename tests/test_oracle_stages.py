@@ -157,3 +157,25 @@ def test_plane_from_three_points():
     pl = ransac_np.plane_from_points(P)[0]
     np.testing.assert_allclose(pl, [0, 0, 1, -1], atol=1e-15)
     assert not ransac_np.plane_from_points(np.zeros((1, 5, 3)))[0].any()     # degenerate -> zero plane
+
+
+# ---- propagation masks (main.py:166-221) ----------------------------------------------------
+@pytest.mark.parametrize("k", range(4))
+def test_propagation_masks_oracle_matches_reference_golden(golden, k):
+    g = golden("propagation.npz")
+    dt, gx, gy, alpha = g[f"params_{k}"]
+    vx, vy, ax, ay = (g[f"{n}_{k}"] for n in ("vx", "vy", "ax", "ay"))
+    got = masks_np.propagation_mask(vx, vy, float(dt), [float(gx), float(gy)], float(alpha))
+    assert got.dtype == np.int64 and np.array_equal(got, g[f"mask_{k}"])
+    got = masks_np.propagation_mask_with_acceleration(vx, vy, ax, ay, float(dt), [float(gx), float(gy)], float(alpha))
+    assert np.array_equal(got, g[f"mask_acc_{k}"])
+    assert 0 < g[f"mask_{k}"].mean() < 1
+
+
+def test_propagation_last_writer_wins():
+    # two sources land on cell (0, 2); the later one in row-major order, (0, 1), must win
+    vx = np.zeros((1, 4), np.float32)
+    vy = np.array([[2.0, 1.0, 1.0, 0.0]], np.float32)    # j' = j + floor(vy): 0->2, 1->2, 2->3, 3->3
+    m = masks_np.propagation_mask(vx, vy, 1.0, [1.0, 1.0], 0.0)
+    # propagated vy: cell 2 <- source 1 (1.0), cell 3 <- source 3 (0.0); cells 0, 1 stay 0
+    assert m.tolist() == [[0, 0, 1, 1]]
