@@ -331,9 +331,11 @@ def extract_cluster_data(labels, indices, vx, vy, engine=None):
 
 
 def flow_to_clusters(bev1, bev2, x_range, y_range, dt, alpha_cont, eps, min_samples, farneback=None, engine=None,
-                     max_clusters=4096):
+                     max_clusters=4096, return_grids=False):
     """The body of the reference's driver loop from the two BEVs to the cluster
-    dictionary the EKF consumes (main.py:577-615), as one device-resident chain."""
+    dictionary the EKF consumes (main.py:577-615), as one device-resident chain.
+    return_grids adds a 4th result: the filtered velocity grids (f64, as the reference holds them)
+    for the artefact writers."""
     eng = engine or default_engine()
     a, b = _bev_to_dev(eng, bev1), _bev_to_dev(eng, bev2)
     H, W = a.shape[-2:]
@@ -351,4 +353,8 @@ def flow_to_clusters(bev1, bev2, x_range, y_range, dt, alpha_cont, eps, min_samp
     clusters = {i: {"centroid": np.array([s[i, 1], s[i, 2]]),
                     "measurement": [s[i, 1], s[i, 2], s[i, 3], s[i, 4]],
                     "eigenvalues": eig[i]} for i in range(ncl) if s[i, 0] > 0}
+    if return_grids:
+        grids = dict(vx_filtered=res.vx_f[0].cpu().numpy().astype(np.float64),
+                     vy_filtered=res.vy_f[0].cpu().numpy().astype(np.float64))
+        return labels, indices, clusters, grids
     return labels, indices, clusters

@@ -6,14 +6,16 @@ Differences from the reference loop, all deliberate:
     and makes every pair fail) are not reproduced; ax / ay were dead values anyway;
   * each frame is preprocessed once and reused as bev2 of pair i-1 and bev1 of pair i
     (the reference preprocesses it twice with different expansion noise);
-  * the matplotlib / CSV / YAML savers are not called (out of scope); the per-pair
-    results are returned instead.
+  * the per-pair results are returned; with ``output_dir`` the data files the reference saves
+    (.npy grids, DBSCAN arrays, track YAML, the two CSVs; artefacts.py) are written too — the
+    matplotlib PNGs are out of scope.
 Per-pair failures are caught and the pair skipped, like the reference's try/except.
 """
 from __future__ import annotations
 
 import numpy as np
 
+from . import artefacts
 from . import main as ops
 from .engine import default_engine
 from .tracker import TrackManager
@@ -24,9 +26,12 @@ DEFAULT_CONFIG = dict(grid_resolution=[0.2, 0.2], x_range=[-20, 20], y_range=[-2
                       dbscan_params=dict(eps=5.0, min_samples=3))
 
 
-def process_clouds(clouds, config=None, engine=None, seed=0, ground_masks=None, verbose=False):
+def process_clouds(clouds, config=None, engine=None, seed=0, ground_masks=None, verbose=False, output_dir=None,
+                   save_grids=False):
     """clouds: iterable of float32 (N,4) sweeps of ONE sequence (or .pcd paths).
-    Returns dict(tracks=TrackManager, pairs=[per-pair dict], bevs=[uint8 grids or None])."""
+    Returns dict(tracks=TrackManager, pairs=[per-pair dict], bevs=[uint8 grids or None]).
+    output_dir: also write the reference's per-frame files there (saving_utils.py formats);
+    save_grids adds the filtered velocity grids and the per-cell CSV (large)."""
     cfg = dict(DEFAULT_CONFIG)
     cfg.update(config or {})
     eng = engine or default_engine()
@@ -35,6 +40,14 @@ def process_clouds(clouds, config=None, engine=None, seed=0, ground_masks=None, 
     tm = TrackManager()
     bevs, pairs = [], []
     prev = None
+    if output_dir is not None:
+        import os
+        os.makedirs(output_dir, exist_ok=True)
+        tracks_csv = os.path.join(output_dir, "tracks.csv")
+        cells_csv = os.path.join(output_dir, "filtered_velocities.csv")
+        for f in (tracks_csv, cells_csv):
+            if os.path.exists(f):
+                os.remove(f)   # the reference starts its CSV afresh (main.py:556-558)
     for i, cloud in enumerate(clouds):
         try:
             pts = ops.read_pcd(cloud) if isinstance(cloud, (str, bytes)) else cloud
@@ -46,6 +59,8 @@ def process_clouds(clouds, config=None, engine=None, seed=0, ground_masks=None, 
                 print(f"Error preprocessing frame {i}: {exc}")
             bev = None
         bevs.append(bev)
+        if output_dir is not None and bev is not None:
+            artefacts.save_bev(output_dir, bev, i)
         if i == 0:
             prev = bev
             continue
@@ -55,11 +70,26 @@ def process_clouds(clouds, config=None, engine=None, seed=0, ground_masks=None, 
                 print(f"Invalid BEV grid for frames {i - 1} and {i}. Skipping.")
         else:
             try:
-                labels, indices, clusters = ops.flow_to_clusters(prev, bev, cfg["x_range"], cfg["y_range"], cfg["dt"],
-                                                                 alpha_cont, dbp["eps"], dbp["min_samples"], engine=eng)
+                out = ops.flow_to_clusters(prev, bev, cfg["x_range"], cfg["y_range"], cfg["dt"], alpha_cont,
+                                           dbp["eps"], dbp["min_samples"], engine=eng,
+                                           return_grids=output_dir is not None and save_grids)
+                labels, indices, clusters = out[:3]
                 if len(labels) == 0:
                     raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by DBSCAN.")
                 tm.update(clusters, cfg["dt"])
+                if output_dir is not None:
+                    k = i - 1
+                    if save_grids:
+                        # main.py:600-609: magnitude and curl of the filtered field, as the reference writes them
+                        vxf, vyf = out[3]["vx_filtered"], out[3]["vy_filtered"]
+                        mag = np.sqrt(vxf ** 2 + vyf ** 2)
+                        dvx_dy, _ = np.gradient(vxf)
+                        _, dvy_dx = np.gradient(vyf)
+                        artefacts.save_velocity_grid(output_dir, vxf, vyf, k)
+                        artefacts.save_all_filtered_velocities_to_csv(vxf, vyf, mag, dvy_dx - dvx_dy, k, cells_csv)
+                    artefacts.save_dbscan_results(output_dir, labels, indices, k)
+                    artefacts.save_ekf_tracks(output_dir, tm, k)
+                    artefacts.save_all_velocities_to_csv(tm, k, tracks_csv)
                 rec = dict(index=i - 1, skipped=False, labels=labels, indices=indices, clusters=clusters,
                            tracks=tm.as_array())
             except Exception as exc:

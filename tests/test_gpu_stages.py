@@ -299,12 +299,12 @@ def test_roi_filter_and_expansion_device(engine, golden):
 
 
 # ---- the sequence driver (preprocess -> flow -> clusters -> tracker) ---------------------------------
-def test_sequence_pipeline_tracks_the_mover(engine):
+def test_sequence_pipeline_tracks_the_mover(engine, tmp_path):
     from datmo_using_optical_flow_b200.pipeline import process_clouds
     cfg = dict(grid_resolution=[0.25, 0.25], x_range=[-50.0, 50.0], y_range=[-50.0, 50.0], z_max=2.0,
                roi_bounds=[-50, 50, -50, 50, -3, 1], dt=1.0)
     clouds = [synth.lidar_sweep(3, f, 32, 60_000, 1, dt=0.1) for f in range(4)]
-    out = process_clouds(clouds, cfg, engine=engine, seed=1)
+    out = process_clouds(clouds, cfg, engine=engine, seed=1, output_dir=str(tmp_path), save_grids=True)
     assert len(out["bevs"]) == 4 and all(b is not None and b.shape == (400, 400) for b in out["bevs"])
     assert len(out["pairs"]) == 3
     done = [p for p in out["pairs"] if not p["skipped"]]
@@ -312,3 +312,15 @@ def test_sequence_pipeline_tracks_the_mover(engine):
     for p in done:
         assert len(p["labels"]) == len(p["indices"]) and p["tracks"].shape[1] == 6
         assert set(p["clusters"]) == set(range(len(p["clusters"])))
+    # the reference's per-frame files (saving_utils.py names and dtypes)
+    for f in range(4):
+        assert np.array_equal(np.load(tmp_path / f"bev_frame_{f}.npy"), out["bevs"][f])
+    for p in done:
+        k = p["index"]
+        assert np.array_equal(np.load(tmp_path / f"dbscan_labels_frame_{k}.npy"), p["labels"])
+        assert np.array_equal(np.load(tmp_path / f"dbscan_indices_frame_{k}.npy"), p["indices"])
+        vx = np.load(tmp_path / f"velocity_x_frame_{k}.npy")
+        assert vx.dtype == np.float64 and vx.shape == (400, 400)
+        assert (tmp_path / f"ekf_tracks_frame_{k}.yaml").exists()
+    assert (tmp_path / "tracks.csv").read_text().startswith("Frame Index,Track ID,Linear Velocity")
+    assert (tmp_path / "filtered_velocities.csv").read_text().startswith("Frame Index,Point Index,Filtered X Velocity")

@@ -152,3 +152,71 @@ def test_synth_is_deterministic_and_sized():
     assert 0.3 < ground.mean() < 0.98
     q = synth.lidar_sweep(0, 5, 32, 60_000, 1)
     assert len(q) != len(p) or not np.array_equal(p, q)          # the mover moved
+
+
+# ---- artefact writers (saving_utils.py formats) ---------------------------------------------
+def _fake_tracks():
+    from datmo_using_optical_flow_b200.tracker import Track
+    return {3: Track(state=np.array([10.5, 20.25, 0.125, -0.5])), 7: Track(state=np.array([1.0, 2.0, 3.0, 4.0]))}
+
+
+def test_artefact_writers_formats(tmp_path):
+    import csv
+    import yaml
+    from datmo_using_optical_flow_b200 import artefacts
+    out = str(tmp_path)
+    bev = (np.arange(12, dtype=np.uint8)).reshape(3, 4)
+    artefacts.save_bev(out, bev, 5)
+    assert np.array_equal(np.load(tmp_path / "bev_frame_5.npy"), bev)
+    labels, idx = np.array([0, 0, -1], dtype=np.intp), np.array([[1, 2], [1, 3], [2, 0]], dtype=np.int64)
+    artefacts.save_dbscan_results(out, labels, idx, 5)
+    assert np.array_equal(np.load(tmp_path / "dbscan_labels_frame_5.npy"), labels)
+    assert np.array_equal(np.load(tmp_path / "dbscan_indices_frame_5.npy"), idx)
+    tracks = _fake_tracks()
+    artefacts.save_ekf_tracks(out, tracks, 5)
+    assert yaml.safe_load(open(tmp_path / "ekf_tracks_frame_5.yaml")) == {3: [10.5, 20.25, 0.125, -0.5], 7: [1.0, 2.0, 3.0, 4.0]}
+    csv_file = str(tmp_path / "tracks.csv")
+    artefacts.save_all_velocities_to_csv(tracks, 5, csv_file)
+    artefacts.save_all_velocities_to_csv(tracks, 6, csv_file)      # appends, header once
+    rows = list(csv.reader(open(csv_file)))
+    assert rows[0] == artefacts.TRACK_CSV_HEADER and len(rows) == 5
+    assert rows[1][:2] == ["5", "3"] and float(rows[1][2]) == np.linalg.norm([0.125, -0.5])
+    assert [float(v) for v in rows[1][3:]] == [0.125, -0.5, 20.25]   # x vel, y vel, state[1] ("angular")
+    vx = np.array([[0.0, 0.5], [0.0, 0.0]])
+    vy = np.array([[0.0, 0.0], [-1.0, 0.0]])
+    cells = str(tmp_path / "cells.csv")
+    artefacts.save_all_filtered_velocities_to_csv(vx, vy, np.hypot(vx, vy), vx * 0 + 2.0, 9, cells)
+    rows = list(csv.reader(open(cells)))
+    assert rows[0] == artefacts.CELL_CSV_HEADER
+    assert rows[1] == ["9", "0", "0.5", "0.0", "0.5", "2.0"] and rows[2] == ["9", "1", "0.0", "-1.0", "1.0", "2.0"]
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).reference_available(),
+                    reason="reference tree not mounted")
+def test_artefact_writers_match_reference_savers(tmp_path, monkeypatch):
+    """Byte-for-byte against the reference's own CSV / YAML writers (saving_utils.py:80-103, 17-46, 119-125)."""
+    import sys
+    from datmo_using_optical_flow_b200 import artefacts
+    from oracle import ref_loader
+    ref = ref_loader.load_reference_main()
+    su = sys.modules["saving_utils"]
+    tracks = _fake_tracks()
+    ours, theirs = tmp_path / "ours", tmp_path / "theirs"
+    ours.mkdir(), theirs.mkdir()
+    su.save_all_velocities_to_csv(tracks, 4, str(theirs / "t.csv"))
+    artefacts.save_all_velocities_to_csv(tracks, 4, str(ours / "t.csv"))
+    assert open(ours / "t.csv").read() == open(theirs / "t.csv").read()
+    rng = np.random.default_rng(2)
+    vx = rng.normal(size=(6, 7)) * (rng.uniform(size=(6, 7)) < 0.4)
+    vy = rng.normal(size=(6, 7)) * (vx != 0)
+    su.save_all_filtered_velocities_to_csv(vx, vy, np.hypot(vx, vy), vx - vy, 4, str(theirs / "c.csv"))
+    artefacts.save_all_filtered_velocities_to_csv(vx, vy, np.hypot(vx, vy), vx - vy, 4, str(ours / "c.csv"))
+    assert open(ours / "c.csv").read() == open(theirs / "c.csv").read()
+    # save_ekf_tracks: the YAML half (the plotting half needs matplotlib, stubbed to no-ops here)
+    plt = sys.modules["matplotlib.pyplot"]
+    for name in ("figure", "plot", "quiver", "title", "xlabel", "ylabel", "legend", "grid", "savefig", "close"):
+        monkeypatch.setattr(plt, name, lambda *a, **k: None, raising=False)
+    monkeypatch.setattr(su, "output_dir", str(theirs))
+    su.save_ekf_tracks(tracks, 4)
+    artefacts.save_ekf_tracks(str(ours), tracks, 4)
+    assert open(ours / "ekf_tracks_frame_4.yaml").read() == open(theirs / "ekf_tracks_frame_4.yaml").read()
