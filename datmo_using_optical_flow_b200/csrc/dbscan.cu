@@ -703,6 +703,8 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
         }
         DATMO_POST_LAUNCH(h);
         if (r >= 1) {
+            // (going straight to k_union_near without this atomics-free pass was measured: the union
+            // pass grows from 0.28 to 1.24 ms per 32 pairs)
             {
                 LaunchScope ls(h, dbg_tag(2));
                 k_link_near<<<g4, 256, 0, h->stream>>>(vx_f, vy_f, state, H, W, r, eps2, parent);

@@ -510,7 +510,30 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp(const SrcT* __restr
         }
     }
     __syncthreads();
-    // blurred image at replicate-clamped coordinates (what polyExp's border handling reads)
+    // blurred image at replicate-clamped coordinates (what polyExp's border handling reads).
+    // Tiles whose blurred region needs no clamping (all but the border ring) walk columns: the row
+    // pass of a raw row is computed once and reused by the three blurred rows that read it.
+    const bool no_clamp = x0 - N >= 0 && x0 - N + RW <= w && y0 - N >= 0 && y0 - N + RH <= h;
+    if (no_clamp) {
+        constexpr int CH = 4, RPC = (RH + CH - 1) / CH;  // row chunks per column, rows per chunk
+        for (int i = tid; i < CH * RW; i += P0_THREADS) {
+            const int ch = i / RW, xx = i - ch * RW;
+            const int r0 = ch * RPC;
+            const float* c = sS + (r0 + 1) * SWS + (xx + OX - N);   // raw pixel under blurred (r0, xx)
+            float tm = 0.25f * c[-SWS - 1] + 0.5f * c[-SWS] + 0.25f * c[-SWS + 1];
+            float t0 = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
+#pragma unroll
+            for (int k = 0; k < RPC; ++k) {
+                const int yy = r0 + k;
+                if (yy >= RH) break;
+                c += SWS;
+                const float tp = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
+                sI[yy * RW + xx] = 0.25f * tm + 0.5f * t0 + 0.25f * tp;
+                tm = t0;
+                t0 = tp;
+            }
+        }
+    } else
     for (int i = tid; i < RH * RW; i += P0_THREADS) {
         const int yy = i / RW, xx = i - yy * RW;
         const int gy = min(max(y0 - N + yy, 0), h - 1), gx = min(max(x0 - N + xx, 0), w - 1);
@@ -1258,10 +1281,10 @@ __device__ __forceinline__ void xm_m_phase(float* __restrict__ sM, const float4*
 
 // vertical sums of nc new columns -> window columns vpos0 .. vpos0 + nc - 1
 template <typename T>
-__device__ __forceinline__ void xm_v_phase(const float* sM, float* sV, int vpos0, int ncl2) {
+__device__ __forceinline__ void xm_v_phase(const float* sM, float* sV, int vpos0, int ncl2, int tid) {
     constexpr int PART = T::TY / T::VSPLIT;
     const int ntask = (5 * T::VSPLIT) << ncl2;
-    for (int i = threadIdx.x; i < ntask; i += T::NT) {
+    for (int i = tid; i < ntask; i += T::NT) {
         const int col = i & ((1 << ncl2) - 1), t = i >> ncl2;
         const int part = t % T::VSPLIT, c = t / T::VSPLIT;
         window_sums<T::WIN, PART>(sM + (c * T::RH + part * PART) * T::MS + col, T::MS,
@@ -1273,16 +1296,16 @@ __device__ __forceinline__ void xm_v_phase(const float* sM, float* sV, int vpos0
 // columns 14..45 (where the next group's vertical sums will be written after the solve has read
 // them) and the last 14 window columns move to the front
 template <typename T>
-__device__ __forceinline__ void xm_h_phase(float* sV) {
-    for (int i = threadIdx.x; i < 5 * T::TY; i += T::NT) window_sums_carry<T::WIN, 32>(sV + i * T::VS);  // i = c * TY + row
+__device__ __forceinline__ void xm_h_phase(float* sV, int tid) {
+    for (int i = tid; i < 5 * T::TY; i += T::NT) window_sums_carry<T::WIN, 32>(sV + i * T::VS);  // i = c * TY + row
 }
 
 // 2x2 solve on the raw window sums: norm^2 scales the determinant and both numerators alike
 // (the regulariser 1e-3 belongs to the normalised determinant, as in solve_flow)
 template <typename T>
 __device__ __forceinline__ void xm_solve(const float* sV, float2* __restrict__ fo, int w, int h, int y0, int c0,
-                                         int xlo, int xhi, float norm) {
-    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+                                         int xlo, int xhi, float norm, int tid) {
+    const int lane = tid & 31, wi = tid >> 5;
     const int gx = c0 - T::HM + lane;
     if (gx < xlo || gx >= xhi) return;
     const int rows = min(T::TY, h - y0);
@@ -1329,12 +1352,12 @@ __global__ void __launch_bounds__(T::NT, T::MINB) k_flow_iter_xm(const float* __
         if (prefetch && k + 1 < ngroups) xm_prefetch<T>(r0q, r0s, r1q, r1s, fb, w, h, x0 + 32 * (k + 1), ry0);
         xm_m_phase<T>(sM, r0q, r0s, r1q, r1s, fb, w, h, c0, ry0, ncl2);
         __syncthreads();  // M complete; S(k-1) has read the window columns V(k) overwrites
-        xm_v_phase<T>(sM, sV, lead ? 6 : 14, ncl2);
+        xm_v_phase<T>(sM, sV, lead ? 6 : 14, ncl2, threadIdx.x);
         __syncthreads();
         if (lead) continue;
-        xm_h_phase<T>(sV);
+        xm_h_phase<T>(sV, threadIdx.x);
         __syncthreads();
-        xm_solve<T>(sV, fo, w, h, y0, c0, x0, xhi, norm);
+        xm_solve<T>(sV, fo, w, h, y0, c0, x0, xhi, norm, threadIdx.x);
     }
 }
 
