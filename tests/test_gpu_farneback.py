@@ -105,6 +105,24 @@ def test_stage_flow_iter_fused_equals_unfused(engine):
     assert np.abs(fused - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
 
 
+@pytest.mark.parametrize("H,W", [(20, 33), (46, 32), (47, 65), (93, 513), (140, 31), (61, 1030)])
+def test_stage_flow_iter_awkward_geometries(engine, H, W):
+    """The x-marching kernel's seams: bands of 46 rows, groups of 32 columns, 8-column lead-in / tail,
+    segment ends, images smaller than one band or one group, taps that leave the image."""
+    R0, R1, flow = _layer_inputs(seed=H + W, H=H, W=W)
+    flow[H // 2, W // 2] = (1e9, -1e9)          # saturating float -> int conversion
+    want = fb.blur_solve(fb.update_matrices(R0, R1, flow), 15)
+    fused = host(engine.fb_flow_iter(planar(R0), planar(R1), dev(flow[None]), 15))[0]
+    assert np.abs(fused - want).max() <= 2e-4 * max(1.0, np.abs(want).max()), np.abs(fused - want).max()
+    # batch of two different fields through one launch
+    flow2 = np.stack([flow, flow[::-1, ::-1].copy()])
+    R0b = np.stack([R0, R0]); R1b = np.stack([R1, R1])
+    got = host(engine.fb_flow_iter(dev(np.moveaxis(R0b, -1, 1).copy()), dev(np.moveaxis(R1b, -1, 1).copy()), dev(flow2), 15))
+    assert np.array_equal(got[0], fused)
+    want2 = fb.blur_solve(fb.update_matrices(R0, R1, flow2[1]), 15)
+    assert np.abs(got[1] - want2).max() <= 2e-4 * max(1.0, np.abs(want2).max())
+
+
 def test_stage_upsample_flow(engine):
     rng = np.random.default_rng(0)
     f = rng.uniform(-3, 3, (36, 41, 2)).astype(np.float32)
