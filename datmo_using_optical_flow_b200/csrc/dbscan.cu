@@ -400,16 +400,36 @@ __global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx,
         const int lane = threadIdx.x & 31;
         const int xw0 = x - lane;  // first column of this warp
         int lo = 0x7fffffff, hi = -1;
-        for (int dr = -r; dr <= 0; ++dr) {
-            const int yy = y + dr;
-            if (yy < 0) continue;
-            const int32_t* prow = par + yy * W;
-            for (int cx = xw0 - r + lane; cx <= xw0 + 31 + r; cx += 32) {
-                if (cx < 0 || cx >= W) continue;
-                const int p = prow[cx];
-                if (p >= 0) {
-                    lo = min(lo, p);
-                    hi = max(hi, p);
+        constexpr int QR = 8;  // windows up to this radius fetch the whole footprint before looking at any of it
+        if (r <= QR) {
+            // 2 (r + 1) independent loads per lane: one memory latency for the footprint, not one per load
+            int p0[QR + 1], p1[QR + 1];
+            const int ca = xw0 - r + lane, cb = ca + 32;
+            const bool oka = ca >= 0 && ca < W, okb = cb <= xw0 + 31 + r && cb < W;
+#pragma unroll
+            for (int t = 0; t <= QR; ++t) {
+                const int yy = y - t;
+                const bool row = t <= r && yy >= 0;
+                p0[t] = row && oka ? par[yy * W + ca] : -1;
+                p1[t] = row && okb ? par[yy * W + cb] : -1;
+            }
+#pragma unroll
+            for (int t = 0; t <= QR; ++t) {
+                if (p0[t] >= 0) lo = min(lo, p0[t]), hi = max(hi, p0[t]);
+                if (p1[t] >= 0) lo = min(lo, p1[t]), hi = max(hi, p1[t]);
+            }
+        } else {
+            for (int dr = -r; dr <= 0; ++dr) {
+                const int yy = y + dr;
+                if (yy < 0) continue;
+                const int32_t* prow = par + yy * W;
+                for (int cx = xw0 - r + lane; cx <= xw0 + 31 + r; cx += 32) {
+                    if (cx < 0 || cx >= W) continue;
+                    const int p = prow[cx];
+                    if (p >= 0) {
+                        lo = min(lo, p);
+                        hi = max(hi, p);
+                    }
                 }
             }
         }
@@ -426,15 +446,36 @@ __global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx,
         if (yy < 0) continue;
         const int dc_lo = max(-r, -x), dc_hi = dr == 0 ? -1 : min(r, W - 1 - x);
         const int32_t* prow = par + yy * W + x;
-        for (int dc = dc_lo; dc <= dc_hi; ++dc) {
-            // parent is -1 for anything that is not a core cell, so one load filters
-            // "not core", "same pass-1 tree" and "tree already joined"
-            const int pq = prow[dc];
-            if (pq < 0 || pq == my_root || pq == joined) continue;
-            const int q = yy * W + x + dc;
-            if (within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2)) {
-                uf_union(par, o, q);
-                joined = pq;
+        // parent is -1 for anything that is not a core cell, so one load filters
+        // "not core", "same pass-1 tree" and "tree already joined"
+        constexpr int QR = 8;
+        if (r <= QR) {
+            // the row's candidates are fetched together (independent loads), then examined
+            int pq[2 * QR + 1];
+#pragma unroll
+            for (int t = 0; t < 2 * QR + 1; ++t) {
+                const int dc = t - QR;
+                pq[t] = dc >= dc_lo && dc <= dc_hi ? prow[dc] : -1;
+            }
+#pragma unroll
+            for (int t = 0; t < 2 * QR + 1; ++t) {
+                if (pq[t] < 0 || pq[t] == my_root || pq[t] == joined) continue;
+                const int dc = t - QR;
+                const int q = yy * W + x + dc;
+                if (within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2)) {
+                    uf_union(par, o, q);
+                    joined = pq[t];
+                }
+            }
+        } else {
+            for (int dc = dc_lo; dc <= dc_hi; ++dc) {
+                const int pq = prow[dc];
+                if (pq < 0 || pq == my_root || pq == joined) continue;
+                const int q = yy * W + x + dc;
+                if (within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2)) {
+                    uf_union(par, o, q);
+                    joined = pq;
+                }
             }
         }
     }
