@@ -490,23 +490,52 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp(const SrcT* __restr
     // raw frame -> shared.  Tiles whose raw region lies inside the image (all but the border ring)
     // move 4 pixels per load; border tiles reflect (BORDER_REFLECT_101) pixel by pixel.
     if (ox >= 0 && ox + NWD * 4 <= w && oy >= 0 && oy + SHS <= h && (w & 3) == 0) {
-        for (int i = tid; i < SHS * NWD; i += P0_THREADS) {
-            const int yy = i / NWD, wd = i - yy * NWD;
-            const SrcT* p = sb + static_cast<size_t>(oy + yy) * w + ox + wd * 4;
-            float4 v;
-            if (sizeof(SrcT) == 1) {
-                const uchar4 u = *reinterpret_cast<const uchar4*>(p);
-                v = make_float4(u.x, u.y, u.z, u.w);
-            } else {
-                v = *reinterpret_cast<const float4*>(p);
+        // every thread's loads are issued before the first store (one memory latency per tile, not one per trip)
+        constexpr int TRIPS = (SHS * NWD + P0_THREADS - 1) / P0_THREADS;
+        float4 v[TRIPS];
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * P0_THREADS;
+            if (i < SHS * NWD) {
+                const int yy = i / NWD, wd = i - yy * NWD;
+                const SrcT* p = sb + static_cast<size_t>(oy + yy) * w + ox + wd * 4;
+                if (sizeof(SrcT) == 1) {
+                    const uchar4 u = *reinterpret_cast<const uchar4*>(p);
+                    v[t] = make_float4(u.x, u.y, u.z, u.w);
+                } else {
+                    v[t] = *reinterpret_cast<const float4*>(p);
+                }
             }
-            *reinterpret_cast<float4*>(sS + yy * SWS + wd * 4) = v;
+        }
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * P0_THREADS;
+            if (i < SHS * NWD) {
+                const int yy = i / NWD, wd = i - yy * NWD;
+                *reinterpret_cast<float4*>(sS + yy * SWS + wd * 4) = v[t];
+            }
         }
     } else {
-        for (int i = tid; i < SHS * NWD * 4; i += P0_THREADS) {
-            const int yy = i / (NWD * 4), xx = i - yy * (NWD * 4);
-            const int gy = reflect101(oy + yy, h), gx = reflect101(ox + xx, w);
-            sS[yy * SWS + xx] = load_px(sb + static_cast<size_t>(gy) * w + gx);
+        // border ring: reflect pixel by pixel, four independent loads per trip
+        for (int i0 = tid; i0 < SHS * NWD * 4; i0 += 4 * P0_THREADS) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * P0_THREADS;
+                if (i < SHS * NWD * 4) {
+                    const int yy = i / (NWD * 4), xx = i - yy * (NWD * 4);
+                    const int gy = reflect101(oy + yy, h), gx = reflect101(ox + xx, w);
+                    v[u] = load_px(sb + static_cast<size_t>(gy) * w + gx);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * P0_THREADS;
+                if (i < SHS * NWD * 4) {
+                    const int yy = i / (NWD * 4), xx = i - yy * (NWD * 4);
+                    sS[yy * SWS + xx] = v[u];
+                }
+            }
         }
     }
     __syncthreads();
