@@ -469,11 +469,17 @@ __global__ void __launch_bounds__(PE_THREADS) k_polyexp(const float* __restrict_
 // Register-blocked: a thread produces 4 vertically adjacent r-values, then 4 horizontally
 // adjacent outputs (shared loads as float4), with the tap count a compile-time constant.
 // ------------------------------------------------------------------------------------
-constexpr int P0_TX = 64, P0_TY = 16, P0_THREADS = 256;
+constexpr int P0_TX = 64, P0_THREADS = 256;
+// tile height: as tall as the 48 KB of static shared memory allow (the blur halo shrinks with it)
+template <int N>
+struct P0Tile {
+    static constexpr int TY = N <= 5 ? 24 : 16;
+};
 
 template <typename SrcT, int N>
 __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp(const SrcT* __restrict__ src, float* __restrict__ R,
                                                              int w, int h, int imgs_per_array, PolyCoef pc) {
+    constexpr int P0_TY = P0Tile<N>::TY;
     constexpr int RW = P0_TX + 2 * N, RH = P0_TY + 2 * N;  // blurred-image region
     constexpr int OX = (N + 1 + 3) & ~3;                   // raw region starts OX columns left of the tile (x4)
     constexpr int NWD = (P0_TX + OX + N + 1 + 3) / 4;      // 4-pixel words per raw row
@@ -1470,7 +1476,7 @@ int flow_tile_choice() {
 bool pyr0_polyexp_supported(int poly_n) { return (poly_n == 5 || poly_n == 7) && !getenv("DATMO_NO_PYR0_FUSION"); }
 
 int launch_pyr0_polyexp(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, float* R, const PolyCoef& pc) {
-    dim3 g(ceil_div(W, P0_TX), ceil_div(H, P0_TY), B);
+    dim3 g(ceil_div(W, P0_TX), ceil_div(H, pc.n <= 5 ? P0Tile<5>::TY : P0Tile<7>::TY), B);
     {
         LaunchScope ls(h, DATMO_TAG_POLYEXP);
         if (dtype == DATMO_U8) {
