@@ -24,7 +24,7 @@ for _ in range(n):
     out = eng.dbscan_grid(vm["vx_f"], vm["vy_f"], vm["valid"], 5.0, 3, cap=524288)
 p = eng.profile_read()
 names = {"pyramid": "flag scans (2x3 kernels)", "polyexp": "k_core", "flow_init": "k_link_near", "flow_iter": "k_flatten (x3)",
-         "velmask": "k_union_far", "dbscan": "k_union_near", "bev": "k_labels", "dbscan": "(untagged)"}
+         "velmask": "k_union_far", "dbscan": "k_union_near", "bev": "k_labels"}
 tot = 0
 for k, v in p.items():
     if v["launches"]:
