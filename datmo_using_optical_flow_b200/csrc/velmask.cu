@@ -93,6 +93,79 @@ __global__ void __launch_bounds__(256) k_velmask(const float2* __restrict__ flow
     }
 }
 
+// The same for four consecutive columns of one row per thread (W % 4 == 0, 16-byte aligned arrays):
+// 16-byte loads of the three flow rows and 16-byte / 4-byte stores of the outputs — a third of the
+// load / store instructions of the column form, which is what bounds this stage.
+__global__ void __launch_bounds__(256) k_velmask4(const float2* __restrict__ flow, int H, int W, float px, float py,
+                                                  float alpha, double s_crit, float s_lo, float s_hi,
+                                                  float* __restrict__ vx_o, float* __restrict__ vy_o,
+                                                  float* __restrict__ ang_o, uint8_t* __restrict__ mask_o,
+                                                  float* __restrict__ vxf_o, float* __restrict__ vyf_o,
+                                                  uint8_t* __restrict__ valid_o, int32_t* __restrict__ n_valid) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, b = blockIdx.z;
+    int n_ok = 0;
+    if (x4 < W) {
+        const size_t base = static_cast<size_t>(b) * H * W;
+        const float2* f = flow + base;
+        const size_t o = static_cast<size_t>(y) * W + x4;
+        const size_t ou = y > 0 ? o - W : o, od = y < H - 1 ? o + W : o;
+        float2 c[6], u[4], d[4];   // c[0] / c[5]: the neighbours left and right of the four cells
+        {
+            const float4 a0 = *reinterpret_cast<const float4*>(f + o), a1 = *reinterpret_cast<const float4*>(f + o + 2);
+            const float4 u0 = *reinterpret_cast<const float4*>(f + ou), u1 = *reinterpret_cast<const float4*>(f + ou + 2);
+            const float4 d0 = *reinterpret_cast<const float4*>(f + od), d1 = *reinterpret_cast<const float4*>(f + od + 2);
+            c[0] = f[o - (x4 > 0)];
+            c[5] = f[o + 3 + (x4 + 4 < W)];
+            c[1] = make_float2(a0.x, a0.y), c[2] = make_float2(a0.z, a0.w);
+            c[3] = make_float2(a1.x, a1.y), c[4] = make_float2(a1.z, a1.w);
+            u[0] = make_float2(u0.x, u0.y), u[1] = make_float2(u0.z, u0.w);
+            u[2] = make_float2(u1.x, u1.y), u[3] = make_float2(u1.z, u1.w);
+            d[0] = make_float2(d0.x, d0.y), d[1] = make_float2(d0.z, d0.w);
+            d[2] = make_float2(d1.x, d1.y), d[3] = make_float2(d1.z, d1.w);
+        }
+        float vx[4], vy[4], cu[4], vxf[4], vyf[4];
+        uint8_t mk[4], ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x4 + j;
+            const float2 cc = c[j + 1], l = c[j], r = c[j + 2];
+            vx[j] = __fmul_rn(cc.x, px), vy[j] = __fmul_rn(cc.y, py);
+            const float dvx_dx = grad1(__fmul_rn(l.x, px), vx[j], __fmul_rn(r.x, px), x, W);
+            const float dvy_dx = grad1(__fmul_rn(l.y, py), vy[j], __fmul_rn(r.y, py), x, W);
+            const float dvx_dy = grad1(__fmul_rn(u[j].x, px), vx[j], __fmul_rn(d[j].x, px), y, H);
+            const float dvy_dy = grad1(__fmul_rn(u[j].y, py), vy[j], __fmul_rn(d[j].y, py), y, H);
+            const float div = __fadd_rn(dvx_dx, dvy_dy);
+            cu[j] = __fsub_rn(dvy_dx, dvx_dy);
+            const int m = (fabsf(div) <= alpha) && (fabsf(cu[j]) <= alpha);
+            vxf[j] = m ? vx[j] : 0.f, vyf[j] = m ? vy[j] : 0.f;
+            const float s32 = vxf[j] * vxf[j] + vyf[j] * vyf[j];   // see k_velmask for the threshold logic
+            int is_valid;
+            if (s32 > s_hi)
+                is_valid = 1;
+            else if (s32 < s_lo)
+                is_valid = 0;
+            else {
+                const double dx = vxf[j], dy = vyf[j];
+                is_valid = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) > s_crit;
+            }
+            mk[j] = static_cast<uint8_t>(m), ok[j] = static_cast<uint8_t>(is_valid);
+            n_ok += is_valid;
+        }
+        if (vx_o) *reinterpret_cast<float4*>(vx_o + base + o) = make_float4(vx[0], vx[1], vx[2], vx[3]);
+        if (vy_o) *reinterpret_cast<float4*>(vy_o + base + o) = make_float4(vy[0], vy[1], vy[2], vy[3]);
+        if (ang_o) *reinterpret_cast<float4*>(ang_o + base + o) = make_float4(cu[0], cu[1], cu[2], cu[3]);
+        if (mask_o) *reinterpret_cast<uchar4*>(mask_o + base + o) = make_uchar4(mk[0], mk[1], mk[2], mk[3]);
+        if (vxf_o) *reinterpret_cast<float4*>(vxf_o + base + o) = make_float4(vxf[0], vxf[1], vxf[2], vxf[3]);
+        if (vyf_o) *reinterpret_cast<float4*>(vyf_o + base + o) = make_float4(vyf[0], vyf[1], vyf[2], vyf[3]);
+        if (valid_o) *reinterpret_cast<uchar4*>(valid_o + base + o) = make_uchar4(ok[0], ok[1], ok[2], ok[3]);
+    }
+    if (n_valid) {
+        n_ok = __reduce_add_sync(0xffffffffu, n_ok);
+        if ((threadIdx.x & 31) == 0 && n_ok) atomicAdd(n_valid + b, n_ok);
+    }
+}
+
 // curl of the FILTERED field (main.py:604-606); f64 arithmetic on f32-representable
 // values, stored as f32 (the reference only writes it to a CSV).
 __global__ void __launch_bounds__(256) k_curl_filtered(const float* __restrict__ vxf, const float* __restrict__ vyf,
@@ -247,11 +320,22 @@ extern "C" int datmo_velocity_mask_dev(datmo_handle_t h, const float* flow, int 
     }
     dim3 g(ceil_div(W, 256), H, batch);
     dim3 gv(ceil_div(W, 256), ceil_div(H, VM_ROWS), batch);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec = (W & 3) == 0 && al16(flow) && al16(vx) && al16(vy) && al16(ang) && al16(vx_f) && al16(vy_f) &&
+                     (reinterpret_cast<uintptr_t>(mask) & 3) == 0 && (reinterpret_cast<uintptr_t>(valid) & 3) == 0;
     {
         LaunchScope ls(h, DATMO_TAG_VELMASK);
-        k_velmask<<<gv, 256, 0, h->stream>>>(reinterpret_cast<const float2*>(flow), H, W, static_cast<float>(px_x),
-                                            static_cast<float>(px_y), static_cast<float>(alpha_cont), s_crit, s_lo, s_hi, vx, vy,
-                                            ang, mask, vx_f, vy_f, valid, n_valid);
+        if (vec) {
+            dim3 g4(ceil_div(W, 1024), H, batch);
+            k_velmask4<<<g4, 256, 0, h->stream>>>(reinterpret_cast<const float2*>(flow), H, W,
+                                                  static_cast<float>(px_x), static_cast<float>(px_y),
+                                                  static_cast<float>(alpha_cont), s_crit, s_lo, s_hi, vx, vy, ang, mask,
+                                                  vx_f, vy_f, valid, n_valid);
+        } else {
+            k_velmask<<<gv, 256, 0, h->stream>>>(reinterpret_cast<const float2*>(flow), H, W, static_cast<float>(px_x),
+                                                 static_cast<float>(px_y), static_cast<float>(alpha_cont), s_crit, s_lo,
+                                                 s_hi, vx, vy, ang, mask, vx_f, vy_f, valid, n_valid);
+        }
     }
     DATMO_POST_LAUNCH(h);
     if (ang_f) {
