@@ -521,8 +521,41 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp(const SrcT* __restr
                 *reinterpret_cast<float4*>(sS + yy * SWS + wd * 4) = v[t];
             }
         }
+    } else if ((w & 3) == 0 && (ox & 3) == 0) {
+        // border ring: rows reflect as a whole (still one 4-pixel load per word); only the words that
+        // straddle the left / right image edge reflect pixel by pixel
+        constexpr int TRIPS = (SHS * NWD + P0_THREADS - 1) / P0_THREADS;
+        float4 v[TRIPS];
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * P0_THREADS;
+            if (i < SHS * NWD) {
+                const int yy = i / NWD, wd = i - yy * NWD;
+                const int gy = reflect101(oy + yy, h), gx0 = ox + wd * 4;
+                const SrcT* row = sb + static_cast<size_t>(gy) * w;
+                if (gx0 >= 0 && gx0 + 3 < w) {
+                    if (sizeof(SrcT) == 1) {
+                        const uchar4 u = *reinterpret_cast<const uchar4*>(row + gx0);
+                        v[t] = make_float4(u.x, u.y, u.z, u.w);
+                    } else {
+                        v[t] = *reinterpret_cast<const float4*>(row + gx0);
+                    }
+                } else {
+                    v[t] = make_float4(load_px(row + reflect101(gx0, w)), load_px(row + reflect101(gx0 + 1, w)),
+                                       load_px(row + reflect101(gx0 + 2, w)), load_px(row + reflect101(gx0 + 3, w)));
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * P0_THREADS;
+            if (i < SHS * NWD) {
+                const int yy = i / NWD, wd = i - yy * NWD;
+                *reinterpret_cast<float4*>(sS + yy * SWS + wd * 4) = v[t];
+            }
+        }
     } else {
-        // border ring: reflect pixel by pixel, four independent loads per trip
+        // ragged widths: reflect pixel by pixel, four independent loads per trip
         for (int i0 = tid; i0 < SHS * NWD * 4; i0 += 4 * P0_THREADS) {
             float v[4];
 #pragma unroll
