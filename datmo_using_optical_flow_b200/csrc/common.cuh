@@ -98,6 +98,22 @@ struct LaunchScope {
     ~LaunchScope();
 };
 
+// Opt-in dynamic shared memory is a per-device function attribute: remember, per call site and per
+// device, the largest size already granted (a process may drive several GPUs through several handles).
+constexpr int DATMO_MAX_DEVICES = 64;
+struct SmemGrant {
+    size_t granted[DATMO_MAX_DEVICES] = {0};
+};
+template <typename Kernel>
+int datmo_grant_smem(datmo_ctx* h, Kernel kernel, size_t bytes, SmemGrant& g) {
+    if (bytes <= 48 * 1024) return DATMO_OK;   // no opt-in needed
+    const int d = h->device >= 0 && h->device < DATMO_MAX_DEVICES ? h->device : 0;
+    if (bytes <= g.granted[d] && h->device < DATMO_MAX_DEVICES) return DATMO_OK;
+    DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    g.granted[d] = bytes;
+    return DATMO_OK;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

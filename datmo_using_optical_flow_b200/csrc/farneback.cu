@@ -1447,25 +1447,17 @@ int launch_pyr(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, co
     const int pr = L.ksize >> 1;
     const size_t smem = static_cast<size_t>(PYR_ROWS) * (((pr + 3) & ~3) + ((W + pr + 1 + 3) & ~3)) * sizeof(float);
     DATMO_REQUIRE(h, smem <= 227 * 1024, "image too wide for the pyramid row staging");
-    static size_t configured_u8 = 48 * 1024, configured_f32 = 48 * 1024;
+    static SmemGrant grant_u8, grant_f32;
     dim3 g1(ceil_div(H, PYR_ROWS), B);
     const int vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0;
     {
         if (dtype == DATMO_U8) {
-            if (smem > configured_u8) {
-                DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_pyr_h<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         static_cast<int>(smem)));
-                configured_u8 = smem;
-            }
+            DATMO_TRY(datmo_grant_smem(h, k_pyr_h<uint8_t>, smem, grant_u8));
             LaunchScope ls(h, DATMO_TAG_PYRAMID);
             k_pyr_h<uint8_t><<<g1, 256, smem, h->stream>>>(static_cast<const uint8_t*>(img), T, H, W, L.w, gk, L.ksize,
                                                            hx, hf, vec);
         } else {
-            if (smem > configured_f32) {
-                DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_pyr_h<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         static_cast<int>(smem)));
-                configured_f32 = smem;
-            }
+            DATMO_TRY(datmo_grant_smem(h, k_pyr_h<float>, smem, grant_f32));
             LaunchScope ls(h, DATMO_TAG_PYRAMID);
             k_pyr_h<float><<<g1, 256, smem, h->stream>>>(static_cast<const float*>(img), T, H, W, L.w, gk, L.ksize, hx,
                                                          hf, vec);
@@ -1485,12 +1477,8 @@ int launch_polyexp(datmo_ctx* h, const float* I, float* R, int w, int hh, int B,
                    const PolyCoef& pc) {
     int RW = PE_TX + 2 * pc.n, RH = PE_TY + 2 * pc.n;
     size_t smem = static_cast<size_t>(RH * RW + 3 * PE_TY * RW) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(smem)));
-        configured = smem;
-    }
+    static SmemGrant grant;
+    DATMO_TRY(datmo_grant_smem(h, k_polyexp, smem, grant));
     dim3 g(ceil_div(w, PE_TX), ceil_div(hh, PE_TY), B);
     {
         LaunchScope ls(h, DATMO_TAG_POLYEXP);
@@ -1532,13 +1520,8 @@ template <int TX, int TY, int NT, int MINB, bool FUSED>
 int launch_flow_iter_w(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, const float* Min,
                        float* flow_out, int w, int hh, int B, float norm) {
     using T = FlowTile<TX, TY, 15, NT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter_w<TX, TY, 15, NT, MINB, FUSED>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(T::SMEM)));
-        attr_set = true;
-    }
+    static SmemGrant grant;
+    DATMO_TRY(datmo_grant_smem(h, k_flow_iter_w<TX, TY, 15, NT, MINB, FUSED>, T::SMEM, grant));
     dim3 g(ceil_div(w, TX), ceil_div(hh, TY), B);
     {
         LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
@@ -1567,12 +1550,8 @@ int xm_pick_segment(int w, int bands, int B, int slots) {
 template <typename T>
 int launch_flow_iter_xm(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, float* flow_out, int w,
                         int hh, int B, float norm) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter_xm<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(T::SMEM)));
-        attr_set = true;
-    }
+    static SmemGrant grant;
+    DATMO_TRY(datmo_grant_smem(h, k_flow_iter_xm<T>, T::SMEM, grant));
     const int bands = ceil_div(hh, T::TY);
     static const int seg_env = getenv("DATMO_XM_SEG") ? atoi(getenv("DATMO_XM_SEG")) : 0;
     const int seg = seg_env > 0 ? ((seg_env + 31) & ~31) : xm_pick_segment(w, bands, B, h->sm_count * T::MINB);
@@ -1604,12 +1583,8 @@ int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float
     }
     size_t smem = flow_iter_smem(m);
     DATMO_REQUIRE(h, smem <= 227 * 1024, "winsize too large for the flow-iteration tile");
-    static size_t configured = 0;
-    if (smem > configured) {
-        DATMO_CHECK_CUDA(h, cudaFuncSetAttribute(k_flow_iter<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(smem)));
-        configured = smem;
-    }
+    static SmemGrant grant;
+    DATMO_TRY(datmo_grant_smem(h, k_flow_iter<FUSED>, smem, grant));
     dim3 g(ceil_div(w, FI_TX), ceil_div(hh, FI_TY), B);
     {
         LaunchScope ls(h, DATMO_TAG_FLOW_ITER);

@@ -257,3 +257,22 @@ def test_cfg4_high_res_2048_poly7_ten_iterations(engine):
     assert d.max() <= 1e-3 and d.mean() <= 1e-5, (d.max(), d.mean())
     core = got[128:-128, 128:-128]
     assert abs(np.median(core[..., 0]) - 3) < 0.05 and abs(np.median(core[..., 1]) - 2) < 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(engine):
+    """Opt-in shared memory is a per-device function attribute: a second handle on another GPU must get
+    its own grant (a process-wide flag would make its launches fail)."""
+    from datmo_using_optical_flow_b200.engine import Engine
+    a, b = synth.textured_pair(8, 150, 170)
+    want = host(engine.farneback(dev(a), dev(b)))[0]
+    eng1 = Engine(1)
+    try:
+        with torch.cuda.device(1):
+            got = eng1.farneback(torch.from_numpy(a).cuda(1), torch.from_numpy(b).cuda(1))
+            eng1.synchronize()
+            got = got.cpu().numpy()[0]
+    finally:
+        eng1.close()
+    assert np.array_equal(got, want)
