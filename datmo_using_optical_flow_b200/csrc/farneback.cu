@@ -281,7 +281,8 @@ __device__ __forceinline__ void r_out(float* R, int B, int bz, size_t n, float4*
 // Horizontal pass: a CTA stages PYR_ROWS source rows in shared memory as f32 (BORDER_REFLECT_101
 // applied while staging, 16 pixels per load) and every thread produces one output column for all
 // of them.  Arithmetic (order of the f32 tap sums, fp64 blend) is that of cv2's blur-then-resize.
-constexpr int PYR_ROWS = 4;
+constexpr int PYR_ROWS = 8;    // source rows staged by one CTA of the horizontal pass
+constexpr int PYR_VROWS = 4;   // output rows per thread of the vertical pass
 
 // four pixels -> one 16-byte shared store (consecutive lanes, consecutive chunks: conflict-free)
 __device__ __forceinline__ float4 load4_px(const uint8_t* p) {
@@ -348,40 +349,40 @@ __global__ void __launch_bounds__(256) k_pyr_h(const SrcT* __restrict__ src, flo
     }
 }
 
-// Vertical pass: a thread owns an output column and PYR_ROWS consecutive output rows whose tap
+// Vertical pass: a thread owns an output column and PYR_VROWS consecutive output rows whose tap
 // chains are independent, so their loads overlap.
 __global__ void __launch_bounds__(128) k_pyr_v(const float* __restrict__ T, float* __restrict__ out, int H, int w,
                                                int h, const float* __restrict__ kern, int ksize,
                                                const int* __restrict__ y0tab, const double* __restrict__ ftab) {
     const int xo = blockIdx.x * blockDim.x + threadIdx.x;
-    const int yo0 = blockIdx.y * PYR_ROWS, b = blockIdx.z;
+    const int yo0 = blockIdx.y * PYR_VROWS, b = blockIdx.z;
     if (xo >= w) return;
     const float* base = T + static_cast<size_t>(b) * H * w + xo;
-    int ys[PYR_ROWS];
-    float a0[PYR_ROWS], a1[PYR_ROWS];
+    int ys[PYR_VROWS];
+    float a0[PYR_VROWS], a1[PYR_VROWS];
 #pragma unroll
-    for (int rr = 0; rr < PYR_ROWS; ++rr) {
+    for (int rr = 0; rr < PYR_VROWS; ++rr) {
         ys[rr] = y0tab[min(yo0 + rr, h - 1)];
         a0[rr] = 0.f, a1[rr] = 0.f;
     }
     for (int i = 0; i <= ksize; ++i) {
         // source row ys + i feeds tap i of a0 and tap i - 1 of a1: one load for both
         const float k0 = i < ksize ? kern[i] : 0.f, k1 = i > 0 ? kern[i - 1] : 0.f;
-        float v[PYR_ROWS];
+        float v[PYR_VROWS];
 #pragma unroll
-        for (int rr = 0; rr < PYR_ROWS; ++rr) {
+        for (int rr = 0; rr < PYR_VROWS; ++rr) {
             int y = ys[rr] + i;
             if (static_cast<unsigned>(y) >= static_cast<unsigned>(H)) y = reflect101(y, H);
             v[rr] = base[static_cast<size_t>(y) * w];
         }
 #pragma unroll
-        for (int rr = 0; rr < PYR_ROWS; ++rr) {
+        for (int rr = 0; rr < PYR_VROWS; ++rr) {
             if (i < ksize) a0[rr] = fmaf(k0, v[rr], a0[rr]);
             if (i > 0) a1[rr] = fmaf(k1, v[rr], a1[rr]);
         }
     }
 #pragma unroll
-    for (int rr = 0; rr < PYR_ROWS; ++rr) {
+    for (int rr = 0; rr < PYR_VROWS; ++rr) {
         const int yo = yo0 + rr;
         if (yo < h) {
             const double fy = ftab[yo];
@@ -1464,7 +1465,7 @@ int launch_pyr(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, co
         }
     }
     DATMO_POST_LAUNCH(h);
-    dim3 g2(ceil_div(L.w, 128), ceil_div(L.h, PYR_ROWS), B);
+    dim3 g2(ceil_div(L.w, 128), ceil_div(L.h, PYR_VROWS), B);
     {
         LaunchScope ls(h, DATMO_TAG_PYRAMID);
         k_pyr_v<<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, gk, L.ksize, vy, vf);
