@@ -359,7 +359,7 @@ __device__ __forceinline__ void union_near_cell(int x, int y, int b, const float
     for (int k = 0; k < 4; ++k) {
         if (pq[k] < 0 || pq[k] == my_root || pq[k] == joined) continue;
         if (within_eps(ndr[k], ndc[k], vx0, vy0, nvx[k], nvy[k], eps2)) {
-            uf_union(par, o, (y + ndr[k]) * W + x + ndc[k]);
+            uf_union(par, my_root, pq[k]);  // both are members of the two trees: start the finds one hop up
             joined = pq[k];
         }
     }
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx,
                 const int dc = t - QR;
                 const int q = yy * W + x + dc;
                 if (within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2)) {
-                    uf_union(par, o, q);
+                    uf_union(par, my_root, pq[t]);  // members of the two trees, one hop closer to the roots
                     joined = pq[t];
                 }
             }
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx,
                 if (pq < 0 || pq == my_root || pq == joined) continue;
                 const int q = yy * W + x + dc;
                 if (within_eps(dr, dc, vx0, vy0, vx[base + q], vy[base + q], eps2)) {
-                    uf_union(par, o, q);
+                    uf_union(par, my_root, pq);
                     joined = pq;
                 }
             }
