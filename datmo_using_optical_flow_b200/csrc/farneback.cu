@@ -293,13 +293,16 @@ __device__ __forceinline__ float4 load4_px(const uint8_t* p) {
 __device__ __forceinline__ float4 load4_px(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 template <typename SrcT>
-__global__ void __launch_bounds__(256) k_pyr_h(const SrcT* __restrict__ src, float* __restrict__ T, int H, int W,
-                                               int w, const float* __restrict__ kern, int ksize,
+__global__ void __launch_bounds__(256) k_pyr_h(const SrcT* __restrict__ src0, const SrcT* __restrict__ src1,
+                                               int n0, float* __restrict__ T, int H, int W, int w,
+                                               const float* __restrict__ kern, int ksize,
                                                const int* __restrict__ x0tab, const double* __restrict__ ftab,
                                                int vec) {
     extern __shared__ __align__(16) float srow[];  // [PYR_ROWS][SW]; element LM + c of a row is source column c
     const int r = ksize >> 1, LM = (r + 3) & ~3, SW = LM + ((W + r + 1 + 3) & ~3);
     const int y0 = blockIdx.x * PYR_ROWS, b = blockIdx.y;
+    // images 0 .. n0-1 come from src0, the rest from src1 (prev and next frames in one launch)
+    const SrcT* src = b < n0 ? src0 : src1 - static_cast<size_t>(n0) * H * W;
     if (vec) {
         // interior, four pixels per thread and trip (W % 4 == 0 and a suitably aligned image)
         const int per_row = W >> 2;
@@ -1438,8 +1441,10 @@ size_t flow_iter_smem(int m) {
 // ------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------
-int launch_pyr(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, const FbLayer& L, const float* d_tab,
-               float* T, float* out) {
+// img1 != nullptr: a second array of B images handled by the same two launches (T and out then hold
+// 2 B images: the caller checks that T is large enough)
+int launch_pyr(datmo_ctx* h, const void* img, const void* img1, int dtype, int H, int W, int B, const FbLayer& L,
+               const float* d_tab, float* T, float* out) {
     const double* hf = reinterpret_cast<const double*>(d_tab);
     const double* vf = hf + L.w;
     const int* hx = reinterpret_cast<const int*>(vf + L.h);
@@ -1449,23 +1454,26 @@ int launch_pyr(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, co
     const size_t smem = static_cast<size_t>(PYR_ROWS) * (((pr + 3) & ~3) + ((W + pr + 1 + 3) & ~3)) * sizeof(float);
     DATMO_REQUIRE(h, smem <= 227 * 1024, "image too wide for the pyramid row staging");
     static SmemGrant grant_u8, grant_f32;
-    dim3 g1(ceil_div(H, PYR_ROWS), B);
-    const int vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0;
+    const int nimg = img1 ? 2 * B : B;
+    dim3 g1(ceil_div(H, PYR_ROWS), nimg);
+    const int vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(img1) & 15) == 0;
     {
         if (dtype == DATMO_U8) {
             DATMO_TRY(datmo_grant_smem(h, k_pyr_h<uint8_t>, smem, grant_u8));
             LaunchScope ls(h, DATMO_TAG_PYRAMID);
-            k_pyr_h<uint8_t><<<g1, 256, smem, h->stream>>>(static_cast<const uint8_t*>(img), T, H, W, L.w, gk, L.ksize,
-                                                           hx, hf, vec);
+            k_pyr_h<uint8_t><<<g1, 256, smem, h->stream>>>(static_cast<const uint8_t*>(img),
+                                                           static_cast<const uint8_t*>(img1), B, T, H, W, L.w, gk,
+                                                           L.ksize, hx, hf, vec);
         } else {
             DATMO_TRY(datmo_grant_smem(h, k_pyr_h<float>, smem, grant_f32));
             LaunchScope ls(h, DATMO_TAG_PYRAMID);
-            k_pyr_h<float><<<g1, 256, smem, h->stream>>>(static_cast<const float*>(img), T, H, W, L.w, gk, L.ksize, hx,
-                                                         hf, vec);
+            k_pyr_h<float><<<g1, 256, smem, h->stream>>>(static_cast<const float*>(img), static_cast<const float*>(img1),
+                                                         B, T, H, W, L.w, gk, L.ksize, hx, hf, vec);
         }
     }
     DATMO_POST_LAUNCH(h);
-    dim3 g2(ceil_div(L.w, 128), ceil_div(L.h, PYR_VROWS), B);
+    dim3 g2(ceil_div(L.w, 128), ceil_div(L.h, PYR_VROWS), nimg);
     {
         LaunchScope ls(h, DATMO_TAG_PYRAMID);
         k_pyr_v<<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, gk, L.ksize, vy, vf);
@@ -1723,8 +1731,14 @@ int fb_run_chunk(datmo_ctx* h, const void* prev, const void* next, int dtype, in
             DATMO_TRY(launch_pyr0_polyexp(h, prev, dtype, H, W, B, R0, pc));
             DATMO_TRY(launch_pyr0_polyexp(h, next, dtype, H, W, B, R1, pc));
         } else {
-            DATMO_TRY(launch_pyr(h, prev, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I0));
-            DATMO_TRY(launch_pyr(h, next, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I1));
+            if (2 * L.w <= W) {
+                // both frames in one pair of launches: T ([B][H][W] floats) holds 2 B images of width w <= W / 2,
+                // and I1 follows I0 in memory
+                DATMO_TRY(launch_pyr(h, prev, next, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I0));
+            } else {
+                DATMO_TRY(launch_pyr(h, prev, nullptr, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I0));
+                DATMO_TRY(launch_pyr(h, next, nullptr, dtype, H, W, B, L, ws.kern + kern_off[li], ws.T, I1));
+            }
             DATMO_TRY(launch_polyexp(h, ws.I, ws.R, L.w, L.h, 2 * B, B, pc));
         }
         float* fin;
@@ -1918,7 +1932,7 @@ int datmo_fb_pyramid_image_dev(datmo_handle_t h, const void* img, int dtype, int
     float* T = bump.take<float>(static_cast<size_t>(batch) * H * w_out);
     DATMO_CHECK_CUDA(h, cudaMemcpyAsync(d_k, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));  // tab is a stack-lifetime vector
-    return launch_pyr(h, img, dtype, H, W, batch, L, d_k, T, out);
+    return launch_pyr(h, img, nullptr, dtype, H, W, batch, L, d_k, T, out);
 }
 
 int datmo_fb_polyexp_dev(datmo_handle_t h, const float* img, int hh, int ww, int batch, int poly_n, double poly_sigma,
