@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx,
         const int lane = threadIdx.x & 31;
         const int xw0 = x - lane;  // first column of this warp
         int lo = 0x7fffffff, hi = -1;
-        constexpr int QR = 8;  // windows up to this radius fetch the whole footprint before looking at any of it
+        constexpr int QR = 5;  // windows up to this radius (the reference's eps 5) fetch the whole footprint before looking at any of it
         if (r <= QR) {
             // 2 (r + 1) independent loads per lane: one memory latency for the footprint, not one per load
             int p0[QR + 1], p1[QR + 1];
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(256) k_union_far(const float* __restrict__ vx,
         const int32_t* prow = par + yy * W + x;
         // parent is -1 for anything that is not a core cell, so one load filters
         // "not core", "same pass-1 tree" and "tree already joined"
-        constexpr int QR = 8;
+        constexpr int QR = 5;
         if (r <= QR) {
             // the row's candidates are fetched together (independent loads), then examined
             int pq[2 * QR + 1];

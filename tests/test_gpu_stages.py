@@ -130,7 +130,7 @@ def test_dbscan_random_fields_vs_sklearn_batched(engine):
     vx = np.where(rng.uniform(size=(B, H, W)) < 0.2, rng.uniform(-2, 2, (B, H, W)), 0).astype(np.float32)
     vy = np.where(vx != 0, rng.uniform(-2, 2, (B, H, W)), 0).astype(np.float32)
     valid = np.sqrt(vx.astype(np.float64) ** 2 + vy.astype(np.float64) ** 2) > 0.1
-    for eps, ms in [(5.0, 3), (1.0, 2), (2.5, 6), (1.5, 4)]:
+    for eps, ms in [(5.0, 3), (1.0, 2), (2.5, 6), (1.5, 4), (7.5, 5), (0.5, 1)]:   # 7.5: the rolled far-window path; 0.5: r = 0
         n_valid, labels, indices, n_clusters = engine.dbscan_grid(dev(vx), dev(vy), dev(valid.astype(np.uint8)), eps, ms)
         n_valid, labels, indices, n_clusters = (host(t) for t in (n_valid, labels, indices, n_clusters))
         for b in range(B):
