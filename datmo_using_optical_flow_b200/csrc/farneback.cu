@@ -1106,12 +1106,14 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter_w(const float* __restric
 //       appended to a 46-column window of vertical sums whose first 14 columns are carried
 //       over from the previous groups;
 //   H   horizontal 15-sums over the window -> 32 finished output columns (they trail the new
-//       group by 7), written where M was; the thread then moves its row's last 14 window columns
-//       to the front;
-//   S   2x2 solve, float2 store.
-// M evaluations per output pixel: (TY + 14) / TY x (seg + 16) / seg  (1.30 for TY 64, seg 256)
+//       group by 7), in place: output j lands on window column 14 + j and the row's last 14
+//       window columns move to the front (the thread that owns a (channel, row) does both);
+//   S   2x2 solve straight from the window, float2 store; it shares a barrier interval with the
+//       next group's M phase, so a group costs three barriers.
+// M evaluations per output pixel: (TY + 14) / TY x (seg + 16) / seg  (1.35 for TY 46, seg 512)
 // against 1.75 for the 64 x 32 tile kernel above, and the vertical pass never touches a halo
-// column.  Every window sum is still the sum of exactly its own 15 values.
+// column.  Every window sum is still the sum of exactly its own 15 values.  The kernel is bound
+// by the L1 data stage (gathers + shared-memory window sums) and by issue, not by HBM: DESIGN.md §5/§6.
 // ------------------------------------------------------------------------------------
 template <int WIN, int NOUT>
 __device__ __forceinline__ void window_sums(const float* __restrict__ in, const int si, float* __restrict__ out,
