@@ -410,8 +410,9 @@ def run_ours(args):
             "config": workload_config(args, B),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(d2h_total / e2e_steps), "steps": e2e_steps,
-                    "what": "pinned host uint8 pairs -> H2D -> flow..clusters -> D2H of counts, labels, indices, "
-                            "cluster summaries, every step; copies double-buffered against compute; wall clock"},
+                    "what": "pinned host uint8 pairs -> H2D -> flow..clusters -> D2H of counts, labels (int32), "
+                            "indices (row << 16 | col, one int32 per moving cell), cluster summaries, every step; "
+                            "copies double-buffered against compute; wall clock"},
             "gpu_launches": int(lc.item()),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_flow_iter_xm (updateMatrices + 15x15 box sums + 2x2 solve, fused)",

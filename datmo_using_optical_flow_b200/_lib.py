@@ -72,6 +72,7 @@ SIGNATURES = {
     "datmo_velocity_mask_dev": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d] + [_vp] * 9),
     "datmo_propagation_mask_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _vp]),
     "datmo_dbscan_grid_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _i, _vp, _vp, _vp, _vp]),
+    "datmo_pack_indices_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "datmo_cluster_summary_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "datmo_bev_bins": (_i, [_d, _d, _d]),
     "datmo_bev_rasterize_dev": (_i, [_vp, _vp, _i, _i64, _d, _d, _d, _d, _i, _i, _d, _d, _d, _vp]),

@@ -815,3 +815,30 @@ extern "C" int datmo_cluster_summary_dev(datmo_handle_t h, const float* vx_f, co
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
 }
+
+// ---- packed (row, col) for the device-to-host copy -----------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_pack_indices(const int2* __restrict__ indices,
+                                                      const int32_t* __restrict__ n_valid, int cap,
+                                                      uint32_t* __restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= min(n_valid[b], cap)) return;
+    const int2 rc = indices[static_cast<size_t>(b) * cap + i];
+    packed[static_cast<size_t>(b) * cap + i] = (static_cast<uint32_t>(rc.x) << 16) | static_cast<uint32_t>(rc.y);
+}
+}  // namespace
+
+extern "C" int datmo_pack_indices_dev(datmo_handle_t h, const int32_t* indices, const int32_t* n_valid, int cap,
+                                      int batch, uint32_t* packed) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, indices && n_valid && packed && cap >= 1 && batch >= 1, "bad arguments");
+    DATMO_REQUIRE(h, batch <= 65535, "batch must fit a CUDA grid dimension");
+    {
+        LaunchScope ls(h, DATMO_TAG_CLUSTER);
+        dim3 g(ceil_div(cap, 256), batch);
+        k_pack_indices<<<g, 256, 0, h->stream>>>(reinterpret_cast<const int2*>(indices), n_valid, cap, packed);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}

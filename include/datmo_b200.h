@@ -180,6 +180,15 @@ int datmo_cluster_summary_dev(datmo_handle_t h, const float* vx_f, const float* 
                               int batch, int cap, const int32_t* n_valid, const int32_t* labels,
                               const int32_t* indices, int max_clusters, double* summary);
 
+/* ---- compact cell records for the host -------------------------------------------
+ * (row, col) of the first min(n_valid, cap) cells of every frame packed as
+ * (row << 16) | col into one uint32 — a third less to move over PCIe than the int32
+ * pairs when the host reads labels and indices of every moving cell (H, W <= 65535).
+ * indices: int32 [batch][cap][2] as written by datmo_dbscan_grid_dev;
+ * packed: uint32 [batch][cap]. */
+int datmo_pack_indices_dev(datmo_handle_t h, const int32_t* indices, const int32_t* n_valid, int cap,
+                           int batch, uint32_t* packed);
+
 /* ---- BEV rasterisation -------------------------------------------------------------
  * Replaces compute_bev_grid, main.py:98-126.  pts: n points in the given layout;
  * nx, ny = len(np.arange(lo, hi, step)) (datmo_bev_bins).  bev: uint8 [nx][ny],

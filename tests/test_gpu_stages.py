@@ -324,3 +324,36 @@ def test_sequence_pipeline_tracks_the_mover(engine, tmp_path):
         assert (tmp_path / f"ekf_tracks_frame_{k}.yaml").exists()
     assert (tmp_path / "tracks.csv").read_text().startswith("Frame Index,Track ID,Linear Velocity")
     assert (tmp_path / "filtered_velocities.csv").read_text().startswith("Frame Index,Point Index,Filtered X Velocity")
+
+
+@pytest.mark.parametrize("packed", [True, False])
+def test_host_flow_pipeline_matches_device_chain(engine, packed):
+    """The host-buffer entry (bench.py's e2e leg): pinned uint8 in, ragged labels / indices / summaries out,
+    with and without the packed (row << 16 | col) read-back, against the device-resident chain."""
+    from datmo_using_optical_flow_b200.engine import HostFlowPipeline, farneback_params
+    B, H, W = 3, 200, 240
+    pipe = HostFlowPipeline(engine, B, H, W, 0.25, 0.25, 0.2, 5.0, 3, farneback_params(), cap=H * W, max_clusters=256,
+                            packed_indices=packed)
+    batches = [synth.bev_pairs(10 * k, B, H, W) for k in range(3)]
+    pins = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in batches]
+    outs = []
+    pipe.submit(0, *pins[0])
+    for k in range(3):
+        if k + 1 < 3:
+            pipe.submit((k + 1) % 2, *pins[k + 1])
+        nv, ncl, off, lab, idx, summ = pipe.collect(k % 2)
+        outs.append((nv.copy(), ncl.copy(), off.copy(), lab.copy(),
+                     (HostFlowPipeline.unpack_indices(idx) if packed else idx).copy(), summ.copy()))
+    assert pipe.d2h_bytes > 0
+    for k, (a, b) in enumerate(batches):
+        res = engine.flow_pipeline(dev(a), dev(b), 0.25, 0.25, 0.2, 5.0, 3, farneback_params(), cap=H * W,
+                                   max_clusters=256)
+        nv, ncl, off, lab, idx, summ = outs[k]
+        assert np.array_equal(nv, host(res.n_valid)) and np.array_equal(ncl, host(res.n_clusters))
+        for i in range(B):
+            n = int(nv[i])
+            assert np.array_equal(lab[off[i]:off[i] + n], host(res.labels)[i, :n])
+            assert np.array_equal(idx[off[i]:off[i] + n], host(res.indices)[i, :n])
+        kmax = summ.shape[1]
+        # mean vx / vy come from fp64 atomics (summation order varies run to run); the rest is exact
+        assert np.allclose(summ, host(res.summary)[:, :kmax], rtol=1e-12, atol=1e-15, equal_nan=True)
