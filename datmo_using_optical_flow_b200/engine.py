@@ -48,6 +48,7 @@ class FlowPipelineResult:
     n_clusters: torch.Tensor         # [B] i32
     summary: torch.Tensor | None     # [B,max_clusters,8] f64
     cap: int
+    ang_f: torch.Tensor | None = None   # [B,H,W] f32 curl of the filtered field (main.py:604-606), on request
 
 
 class Engine:
@@ -306,17 +307,18 @@ class Engine:
     # -- flow -> clusters, the body of the reference's driver loop (main.py:577-615) --------------
     def flow_pipeline(self, prev, nxt, px_x, px_y, alpha_cont, eps, min_samples, params=None, thresh=0.1,
                       cap: int | None = None, max_clusters: int = 0, keep_flow: bool = True,
-                      flow_buf: torch.Tensor | None = None) -> FlowPipelineResult:
+                      flow_buf: torch.Tensor | None = None, want_ang_f: bool = False) -> FlowPipelineResult:
         with self.on_stream():
             flow = self.farneback(prev, nxt, params, out=flow_buf)
-            vm = self.velocity_mask(flow, px_x, px_y, alpha_cont, thresh, want=("vx_f", "vy_f", "valid"))
+            want = ("vx_f", "vy_f", "valid", "ang_f") if want_ang_f else ("vx_f", "vy_f", "valid")
+            vm = self.velocity_mask(flow, px_x, px_y, alpha_cont, thresh, want=want)
             n_valid, labels, indices, n_clusters = self.dbscan_grid(vm["vx_f"], vm["vy_f"], vm["valid"], eps,
                                                                     min_samples, cap)
             summary = None
             if max_clusters > 0:
                 summary = self.cluster_summary(vm["vx_f"], vm["vy_f"], n_valid, labels, indices, max_clusters)
         return FlowPipelineResult(flow if keep_flow else None, vm["vx_f"], vm["vy_f"], vm["valid"], n_valid, labels,
-                                  indices, n_clusters, summary, labels.shape[1])
+                                  indices, n_clusters, summary, labels.shape[1], vm.get("ang_f"))
 
     # -- BEV / RANSAC / preprocessing -----------------------------------------------------------
     def bev_bins(self, lo: float, hi: float, step: float) -> int:

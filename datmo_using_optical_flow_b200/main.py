@@ -334,15 +334,15 @@ def flow_to_clusters(bev1, bev2, x_range, y_range, dt, alpha_cont, eps, min_samp
                      max_clusters=4096, return_grids=False):
     """The body of the reference's driver loop from the two BEVs to the cluster
     dictionary the EKF consumes (main.py:577-615), as one device-resident chain.
-    return_grids adds a 4th result: the filtered velocity grids (f64, as the reference holds them)
-    for the artefact writers."""
+    return_grids adds a 4th result: the filtered velocity grids, their magnitude and curl (f64, as the
+    reference holds them, main.py:600-606) for the artefact writers."""
     eng = engine or default_engine()
     a, b = _bev_to_dev(eng, bev1), _bev_to_dev(eng, bev2)
     H, W = a.shape[-2:]
     px = (x_range[1] - x_range[0]) / W
     py = (y_range[1] - y_range[0]) / H
     res = eng.flow_pipeline(a, b, px, py, alpha_cont, eps, min_samples, farneback_params(**(farneback or {})),
-                            max_clusters=max_clusters)
+                            max_clusters=max_clusters, want_ang_f=return_grids)
     eng.synchronize()
     n = int(res.n_valid[0].item())
     ncl = min(int(res.n_clusters[0].item()), max_clusters)
@@ -354,7 +354,10 @@ def flow_to_clusters(bev1, bev2, x_range, y_range, dt, alpha_cont, eps, min_samp
                     "measurement": [s[i, 1], s[i, 2], s[i, 3], s[i, 4]],
                     "eigenvalues": eig[i]} for i in range(ncl) if s[i, 0] > 0}
     if return_grids:
-        grids = dict(vx_filtered=res.vx_f[0].cpu().numpy().astype(np.float64),
-                     vy_filtered=res.vy_f[0].cpu().numpy().astype(np.float64))
+        # f64 like the reference's arrays (f32 * int64 mask); magnitude and curl computed on the device
+        vxf, vyf = res.vx_f[0].to(torch.float64), res.vy_f[0].to(torch.float64)
+        grids = dict(vx_filtered=vxf.cpu().numpy(), vy_filtered=vyf.cpu().numpy(),
+                     velocity_magnitude=torch.sqrt(vxf * vxf + vyf * vyf).cpu().numpy(),
+                     angular_velocity=res.ang_f[0].to(torch.float64).cpu().numpy())
         return labels, indices, clusters, grids
     return labels, indices, clusters

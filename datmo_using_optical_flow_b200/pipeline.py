@@ -13,8 +13,6 @@ Per-pair failures are caught and the pair skipped, like the reference's try/exce
 """
 from __future__ import annotations
 
-import numpy as np
-
 from . import artefacts
 from . import main as ops
 from .engine import default_engine
@@ -80,13 +78,12 @@ def process_clouds(clouds, config=None, engine=None, seed=0, ground_masks=None, 
                 if output_dir is not None:
                     k = i - 1
                     if save_grids:
-                        # main.py:600-609: magnitude and curl of the filtered field, as the reference writes them
-                        vxf, vyf = out[3]["vx_filtered"], out[3]["vy_filtered"]
-                        mag = np.sqrt(vxf ** 2 + vyf ** 2)
-                        dvx_dy, _ = np.gradient(vxf)
-                        _, dvy_dx = np.gradient(vyf)
-                        artefacts.save_velocity_grid(output_dir, vxf, vyf, k)
-                        artefacts.save_all_filtered_velocities_to_csv(vxf, vyf, mag, dvy_dx - dvx_dy, k, cells_csv)
+                        # main.py:600-609: the filtered field, its magnitude and curl (all from the device)
+                        g = out[3]
+                        artefacts.save_velocity_grid(output_dir, g["vx_filtered"], g["vy_filtered"], k)
+                        artefacts.save_all_filtered_velocities_to_csv(g["vx_filtered"], g["vy_filtered"],
+                                                                      g["velocity_magnitude"], g["angular_velocity"],
+                                                                      k, cells_csv)
                     artefacts.save_dbscan_results(output_dir, labels, indices, k)
                     artefacts.save_ekf_tracks(output_dir, tm, k)
                     artefacts.save_all_velocities_to_csv(tm, k, tracks_csv)
