@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libdatmo_b200.so")
 STAMP = os.path.join(LIB_DIR, "libdatmo_b200.stamp")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["context.cu", "farneback.cu", "velmask.cu", "dbscan.cu", "bev.cu", "ransac.cu"]
+SOURCES = ["context.cu", "farneback.cu", "velmask.cu", "dbscan.cu", "dbscan_runs.cu", "bev.cu", "ransac.cu"]
 # files whose fp64 arithmetic must round every operation like numpy does (no FMA contraction)
 NO_FMAD = {"ransac.cu"}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

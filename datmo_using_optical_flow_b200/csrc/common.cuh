@@ -121,4 +121,11 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 int datmo_flag_scan(datmo_ctx* h, const uint8_t* flags, int64_t n, int batch, int32_t* block_sums, int32_t* totals,
                     int32_t* rank, int tag, int sparse);
 
+// dbscan_runs.cu: the run-based DBSCAN (1 <= floor(eps) <= 15); called by datmo_dbscan_grid_dev
+bool datmo_dbscan_runs_supported(double eps);
+size_t datmo_dbscan_runs_workspace(int H, int W, int batch);
+int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy_f, const uint8_t* valid, int H, int W,
+                      int batch, double eps, int min_samples, int cap, int32_t* n_valid, int32_t* labels,
+                      int32_t* indices, int32_t* n_clusters, int (*tag)(int));
+
 #define DATMO_POST_LAUNCH(h) DATMO_CHECK_CUDA(h, cudaGetLastError())

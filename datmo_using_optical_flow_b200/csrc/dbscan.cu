@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "dbscan_common.cuh"
 
 namespace {
 
@@ -141,29 +142,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_flag_ranks(const uint8_t* __re
     }
 }
 
-// ---- neighbour predicate ----------------------------------------------------------------
-// eps^2 with an f32 guard band: the f32 evaluation of d2 is within 3e-7 (relative) of the fp64 one,
-// so outside [lo, hi] = eps^2 (1 -+ 2e-6) it decides; only the sliver in between pays for fp64.
-struct EpsTest {
-    double e2;
-    float lo, hi;
-};
-
-__device__ __forceinline__ bool within_eps(int dr, int dc, float vx0, float vy0, float vx1, float vy1,
-                                           const EpsTest& e) {
-    const float fvx = vx0 - vx1, fvy = vy0 - vy1;
-    const float s = static_cast<float>(dr * dr + dc * dc) + fvx * fvx + fvy * fvy;
-    if (s < e.lo) return true;
-    if (s > e.hi) return false;
-    double d2 = static_cast<double>(dr * dr);
-    d2 = __dadd_rn(d2, static_cast<double>(dc * dc));
-    const double dvx = __dsub_rn(static_cast<double>(vx0), static_cast<double>(vx1));
-    const double dvy = __dsub_rn(static_cast<double>(vy0), static_cast<double>(vy1));
-    d2 = __dadd_rn(d2, __dmul_rn(dvx, dvx));
-    d2 = __dadd_rn(d2, __dmul_rn(dvy, dvy));
-    return d2 <= e.e2;
-}
-
 // state: 0 = not valid, 1 = valid non-core, 2 = core.  parent: self for core cells, -1 otherwise.
 __device__ __forceinline__ void core_cell(int x, int y, int b, const float* __restrict__ vx, const float* __restrict__ vy,
                                               const uint8_t* __restrict__ valid, int H, int W, int r, EpsTest eps2,
@@ -239,38 +217,6 @@ __global__ void __launch_bounds__(256) k_core(const float* __restrict__ vx, cons
         return;
     }
     for (int j = 0; j < 4 && x4 + j < W; ++j) core_cell(x4 + j, y, b, vx, vy, valid, H, W, r, eps2, min_samples, state, parent);
-}
-
-// Union-find over int32 cell indices.  Other CTAs link roots concurrently, and L1 is not
-// coherent between SMs, so every read of the forest goes to L2 (__ldcg) and every link is
-// an atomicCAS; a stale L1 line could otherwise make a thread retry the same CAS forever.
-__device__ __forceinline__ int uf_find(int32_t* parent, int a) {
-    int p = __ldcg(parent + a);
-    while (p != a) {
-        int gp = __ldcg(parent + p);
-        if (gp != p) __stcg(parent + a, gp);  // path halving; only ever shortens the path
-        a = p;
-        p = gp;
-    }
-    return a;
-}
-
-__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
-    while (true) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
-        if (a == b) return;
-        if (a < b) {
-            int t = a;
-            a = b;
-            b = t;
-        }
-        // a > b: hang the larger root under the smaller, so a root is always the
-        // minimum index of its component
-        int old = atomicCAS(parent + a, a, b);
-        if (old == a) return;
-        a = old;  // someone linked a first; continue from where it points now
-    }
 }
 
 // Link pass 1 (no atomics): every core cell points at the smallest-index core cell among its
@@ -712,6 +658,12 @@ extern "C" int datmo_dbscan_grid_dev(datmo_handle_t h, const float* vx_f, const 
     DATMO_REQUIRE(h, H <= 65535 && batch <= 65535, "H and batch must fit a CUDA grid dimension");
     DATMO_REQUIRE(h, eps >= 0 && eps < 1024 && min_samples >= 1, "eps / min_samples out of range");
     const int64_t n = static_cast<int64_t>(H) * W;
+    if (datmo_dbscan_runs_supported(eps)) {
+        // the reference's eps (5) and anything else with 1 <= floor(eps) <= 15: row runs on bit planes
+        DATMO_TRY(datmo_ws_reserve(h, datmo_dbscan_runs_workspace(H, W, batch)));
+        return datmo_dbscan_runs(h, h->ws, vx_f, vy_f, valid, H, W, batch, eps, min_samples, cap, n_valid, labels,
+                                 indices, n_clusters, dbg_tag);
+    }
     const int nblk = static_cast<int>(ceil_div64(n, SCAN_ITEMS));
     const int r = static_cast<int>(floor(eps));
     EpsTest eps2;

@@ -142,6 +142,66 @@ def test_dbscan_random_fields_vs_sklearn_batched(engine):
             assert n_clusters[b] == (want.max() + 1 if len(want) and want.max() >= 0 else 0)
 
 
+def _dbscan_fields(rng, B, H, W, kind):
+    if kind == "blobs":       # rectangles with holes, smooth velocities: long runs, few roots
+        valid = np.zeros((B, H, W), bool)
+        for b in range(B):
+            for _ in range(10):
+                y, x = rng.integers(0, H - 5), rng.integers(0, W - 5)
+                valid[b, y:y + rng.integers(2, 14), x:x + rng.integers(2, 40)] = True
+        valid &= rng.uniform(size=(B, H, W)) < 0.97
+        vx = rng.normal(size=(B, H, W)) * 0.4
+        vy = rng.normal(size=(B, H, W)) * 0.4
+    elif kind == "ties":      # integer velocities: d2 lands exactly on eps^2 (dr = eps, dv = 0)
+        valid = rng.uniform(size=(B, H, W)) < 0.5
+        vx = np.round(rng.normal(size=(B, H, W)) * 2.0)
+        vy = np.round(rng.normal(size=(B, H, W)) * 2.0)
+    else:                     # dense noise with large jumps: broken links inside rows
+        valid = rng.uniform(size=(B, H, W)) < 0.8
+        vx = rng.normal(size=(B, H, W)) * 3.0
+        vy = rng.normal(size=(B, H, W)) * 3.0
+    return (vx * valid).astype(np.float32), (vy * valid).astype(np.float32), valid
+
+
+@pytest.mark.parametrize("impl", ["runs", "cells"])
+@pytest.mark.parametrize("kind", ["blobs", "ties", "jumps"])
+def test_dbscan_run_rule_vs_sklearn(engine, kind, impl, monkeypatch):
+    """Both implementations (row runs on bit planes; cell-level passes) against live sklearn on fields
+    that stress the run rule: long runs, exact ties at eps, broken links; widths that are not a
+    multiple of 32 and wider than one 8-word segment."""
+    if impl == "cells":
+        monkeypatch.setenv("DATMO_DBSCAN_CELLS", "1")
+    rng = np.random.default_rng({"blobs": 11, "ties": 12, "jumps": 13}[kind])
+    B, H, W = 4, 61, 300
+    vx, vy, valid = _dbscan_fields(rng, B, H, W, kind)
+    for eps, ms in [(5.0, 3), (1.0, 2), (3.3, 4), (2.0, 5), (15.9, 9)]:
+        n_valid, labels, indices, n_clusters = engine.dbscan_grid(dev(vx), dev(vy), dev(valid.astype(np.uint8)), eps, ms)
+        n_valid, labels, indices, n_clusters = (host(t) for t in (n_valid, labels, indices, n_clusters))
+        for b in range(B):
+            want, widx = dbscan_np.dbscan_clustering_sklearn(vx[b].astype(np.float64), vy[b].astype(np.float64),
+                                                             valid[b], eps, ms)
+            n = n_valid[b]
+            assert n == len(want)
+            assert np.array_equal(indices[b, :n], widx)
+            assert np.array_equal(labels[b, :n], want), (kind, impl, eps, ms, b)
+            assert n_clusters[b] == (want.max() + 1 if want.max() >= 0 else 0)
+
+
+def test_dbscan_bench_density_1024_labels_identical_to_sklearn(engine):
+    """The benchmarked regime: a 1024x1024 synth.bev_pair through the GPU chain (150-260 k moving cells, ~140
+    clusters); the GPU's own vx_f / vy_f / valid fed to the reference's sklearn call must give the same labels."""
+    a, b = synth.bev_pair(1, 1024, 1024)
+    res = engine.flow_pipeline(dev(a)[None], dev(b)[None], 0.1, 0.1, 0.2, 5.0, 3, max_clusters=0)
+    n = int(host(res.n_valid)[0])
+    assert n >= 100_000
+    vx_f, vy_f, valid = host(res.vx_f)[0], host(res.vy_f)[0], host(res.valid)[0].astype(bool)
+    want, widx = dbscan_np.dbscan_clustering_sklearn(vx_f.astype(np.float64), vy_f.astype(np.float64), valid, 5.0, 3)
+    assert n == len(want)
+    assert np.array_equal(host(res.indices)[0, :n], widx)
+    assert np.array_equal(host(res.labels)[0, :n], want)
+    assert int(host(res.n_clusters)[0]) == want.max() + 1
+
+
 def test_dbscan_large_grid_vs_grid_rule_oracle(engine):
     """cfg3-sized grid, sparse moving cells; the oracle grid rule is itself pinned to sklearn on CPU."""
     rng = np.random.default_rng(3)

@@ -107,6 +107,33 @@ def test_dbscan_grid_rule_matches_live_sklearn_random():
         assert np.array_equal(gidx, widx) and np.array_equal(got, want)
 
 
+def test_run_rule_matches_live_sklearn():
+    """The row-run rule the CUDA fast path implements (oracle/dbscan_runs_np.py) against the reference's own
+    sklearn call: sparse noise, blobs with holes, exact ties at eps, large velocity jumps."""
+    from oracle import dbscan_runs_np
+    rng = np.random.default_rng(0)
+    for trial in range(16):
+        H, W = int(rng.integers(20, 50)), int(rng.integers(20, 70))
+        if trial % 4 >= 2:
+            valid = np.zeros((H, W), bool)
+            for _ in range(8):
+                y, x = rng.integers(0, H - 5), rng.integers(0, W - 5)
+                valid[y:y + rng.integers(2, 12), x:x + rng.integers(2, 20)] = True
+            valid &= rng.random((H, W)) < 0.97
+        else:
+            valid = rng.random((H, W)) < [0.15, 0.6][trial % 2]
+        scale = [0.3, 2.0, 4.0, 6.0][(trial // 4) % 4]
+        vx = (rng.standard_normal((H, W)) * scale).astype(np.float32).astype(np.float64)
+        vy = (rng.standard_normal((H, W)) * scale).astype(np.float32).astype(np.float64)
+        if trial % 5 == 0:
+            vx, vy = np.round(vx), np.round(vy)
+        vx, vy = vx * valid, vy * valid
+        for eps, ms in ((5.0, 3), (1.0, 2), (1.5, 3), (3.3, 4), (2.9, 1)):
+            want, widx = dbscan_np.dbscan_clustering_sklearn(vx, vy, valid, eps, ms)
+            got, gidx = dbscan_runs_np.dbscan_runs(vx, vy, valid, eps, ms)
+            assert np.array_equal(gidx, widx) and np.array_equal(got, want), (trial, eps, ms)
+
+
 def test_same_partition_helper():
     assert dbscan_np.same_partition(np.array([0, 0, 1, -1]), np.array([1, 1, 0, -1]))
     assert not dbscan_np.same_partition(np.array([0, 0, 1, -1]), np.array([0, 1, 1, -1]))
