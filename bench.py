@@ -37,14 +37,17 @@ METRIC = "bev_frame_pairs_per_sec"
 UNIT = "pairs/s"
 
 
-def algorithmic_bytes(H, W, fb=FB):
+def algorithmic_bytes(H, W, fb=FB, layers=None):
     """stage-fused model, f32 arrays, each logical array crossing HBM once per
-    producing / consuming stage.  Returns (A per pair, bytes of the flow-iteration launches per pair)."""
-    from oracle import farneback_np
-    layers = farneback_np.level_plan(H, W, fb["pyr_scale"], fb["levels"])
+    producing / consuming stage: A = L*8*N0 + 40*sumN + I*56*sumN + 8*(pixels of every layer but the finest,
+    read by the flow upsampling).  `layers`: [(h, w)] coarsest first, from datmo_farneback_layers.
+    Returns (A per pair, bytes of the flow-iteration launches per pair, layer count)."""
+    if layers is None:
+        from datmo_using_optical_flow_b200.engine import farneback_layers_host
+        layers = farneback_layers_host(H, W, fb)
     N0 = H * W
-    sumN = sum(l["w"] * l["h"] for l in layers)
-    up = sum(l["w"] * l["h"] for l in layers[1:])      # every layer but the coarsest reads an upsampled flow
+    sumN = sum(h * w for h, w in layers)
+    up = sum(h * w for h, w in layers[:-1])
     iters = fb["iterations"]
     A = len(layers) * 8 * N0 + 40 * sumN + iters * 56 * sumN + 8 * up
     return A, iters * 56 * sumN, len(layers)
@@ -138,53 +141,80 @@ class ClockSampler:
 # CPU arm: the reference's call sequence on the host cores
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
+    """One worker process: `repeat` passes of the reference's call sequence over one pair; returns
+    (seconds, moving cells, per-stage seconds {flow, masks, dbscan, clusters})."""
     seed, H, W, repeat = args
     import cv2
     cv2.setNumThreads(1)
     from datmo_using_optical_flow_b200 import synth
-    from oracle import reference_port
+    from oracle import cluster_np, dbscan_np, reference_port
     a, b = synth.bev_pair(seed, H, W)
-    rng = [-0.05 * W, 0.05 * W]
-    t0 = time.perf_counter()
+    xr, yr = [-0.05 * W, 0.05 * W], [-0.05 * H, 0.05 * H]
+    st = dict(flow=0.0, masks=0.0, dbscan=0.0, clusters=0.0)
+    t_all = time.perf_counter()
     n = 0
     for _ in range(repeat):
-        out = reference_port.flow_to_clusters(a, b, rng, [-0.05 * H, 0.05 * H], 1.0, ALPHA_CONT, EPS, MIN_SAMPLES)
-        n += len(out["labels"])
-    return time.perf_counter() - t0, n
-
-
-def cpu_pairs_per_sec(H, W, cores, rounds, seed0=0, pool=None):
-    """`cores` worker processes (cv2 single-threaded in each: OpenCV's Farneback does not scale with
-    threads), one pair per worker per round; returns (pairs/s, wall seconds)."""
-    import multiprocessing as mp
-    own = pool is None
-    if own:
-        pool = mp.get_context("spawn").Pool(cores)
-    try:
+        # reference_port.flow_to_clusters, stage by stage (main.py:577-615)
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(seed0 + i, H, W, rounds) for i in range(cores)])
-        wall = time.perf_counter() - t0
-    finally:
-        if own:
-            pool.close()
-            pool.join()
-    return cores * rounds / wall, wall
+        vx, vy, _ = reference_port.compute_velocity_vectors(a, b, xr, yr, 1.0)
+        t1 = time.perf_counter()
+        mask = reference_port.continuity_mask(vx, vy, ALPHA_CONT)
+        vx_f, vy_f = vx * mask, vy * mask
+        valid = np.sqrt(vx_f ** 2 + vy_f ** 2) > 0.1
+        t2 = time.perf_counter()
+        if not valid.any():     # sklearn raises on an empty array; the reference's try/except skips the pair
+            continue
+        labels, indices = dbscan_np.dbscan_clustering_sklearn(vx_f, vy_f, valid, EPS, MIN_SAMPLES)
+        t3 = time.perf_counter()
+        cluster_np.extract_cluster_data(labels, indices, vx_f, vy_f)
+        t4 = time.perf_counter()
+        st["flow"] += t1 - t0
+        st["masks"] += t2 - t1
+        st["dbscan"] += t3 - t2
+        st["clusters"] += t4 - t3
+        n += len(labels)
+    return time.perf_counter() - t_all, n, st
+
+
+def _cpu_warm(_):
+    """Imports + one tiny pass, so pool start-up is not inside anybody's timed region."""
+    _cpu_worker((0, 96, 96, 1))
+    return os.getpid()
+
+
+def cpu_pool(cores):
+    import multiprocessing as mp
+    pool = mp.get_context("spawn").Pool(cores)
+    pool.map(_cpu_warm, range(cores))
+    return pool
+
+
+def cpu_pairs_per_sec(H, W, cores, rounds, pool, seed0=0):
+    """`cores` worker processes (cv2 single-threaded in each: OpenCV's Farneback does not scale with
+    threads, SURVEY.md §6), one pair per worker per round, on an already warm pool;
+    returns (pairs/s, wall seconds, mean per-stage seconds per pair)."""
+    t0 = time.perf_counter()
+    out = pool.map(_cpu_worker, [(seed0 + i, H, W, rounds) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    stage = {k: sum(o[2][k] for o in out) / (cores * rounds) for k in out[0][2]}
+    return cores * rounds / wall, wall, stage
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
     H = W = args.size
     cores = os.cpu_count() or 1
-    pool = mp.get_context("spawn").Pool(cores)
+    pool = cpu_pool(cores)
+    stage = None
     try:
         for i in range(args.warmup):
-            cpu_pairs_per_sec(H, W, cores, 1, seed0=1000 + i * cores, pool=pool)
+            cpu_pairs_per_sec(H, W, cores, 1, pool, seed0=1000 + i * cores)
         t0 = time.perf_counter()
         for i in range(args.steps):
-            cpu_pairs_per_sec(H, W, cores, 1, seed0=i * cores, pool=pool)
+            _, _, st = cpu_pairs_per_sec(H, W, cores, 1, pool, seed0=i * cores)
+            stage = st if stage is None else {k: stage[k] + st[k] for k in st}
         wall = time.perf_counter() - t0
     finally:
         pool.close()
@@ -198,6 +228,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.batch),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "stage_s": {k: round(v / max(args.steps, 1), 4) for k, v in (stage or {}).items()},
+        "stage_s_what": "mean seconds per pair inside one worker: cv2 Farneback + velocity / continuity mask + "
+                        "threshold / sklearn DBSCAN / cluster summaries",
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -212,6 +245,75 @@ def workload_config(args, batch):
             "size": args.size, "pairs_per_step_per_gpu": batch, "pool_pairs_per_gpu": args.pool,
             "l2": "step working set (~70 MB/pair of f32 planes) and the rotating input pool exceed the 126 MB L2",
             "sharding": "pairs sharded across ranks, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------
+# parity of the benchmarked workload (checker only; outside every timed region)
+# ------------------------------------------------------------------------------------------------
+def parity_block(eng, prev_np, next_np, params, px, py, cap, n_pairs=2):
+    """The first `n_pairs` pairs of a batch through the GPU chain, against the reference's own calls:
+    flow vs cv2.calcOpticalFlowFarneback (reference parameters), the moving-cell mask vs the reference's
+    numpy chain on cv2's flow, and the labels vs sklearn DBSCAN fed the GPU's own vx_f / vy_f / valid
+    (main.py:142, 224-228, 600-609, 257).  Returns the worst case over the pairs."""
+    import cv2
+    import torch
+    from oracle import dbscan_np, reference_port
+    cv2.setNumThreads(0)
+    H, W = prev_np.shape[1:]
+    a = torch.from_numpy(prev_np[:n_pairs]).cuda()
+    b = torch.from_numpy(next_np[:n_pairs]).cuda()
+    res = eng.flow_pipeline(a, b, px, py, ALPHA_CONT, EPS, MIN_SAMPLES, params, cap=cap, max_clusters=0, keep_flow=True)
+    eng.synchronize()
+    flow = res.flow.cpu().numpy()
+    vx_f, vy_f = res.vx_f.cpu().numpy(), res.vy_f.cpu().numpy()
+    valid = res.valid.cpu().numpy().astype(bool)
+    n_valid = res.n_valid.cpu().numpy()
+    labels, indices = res.labels.cpu().numpy(), res.indices.cpu().numpy()
+    out = dict(pairs=n_pairs, flow_max_px=0.0, flow_mean_px=0.0, flow_p999_px=0.0, valid_cells_differing=0,
+               valid_cells=0, labels_identical=True, indices_identical=True, moving_cells_checked=0)
+    xr, yr = [-0.5 * px * W, 0.5 * px * W], [-0.5 * py * H, 0.5 * py * H]
+    for i in range(n_pairs):
+        ref = cv2.calcOpticalFlowFarneback(prev_np[i].astype(np.float32), next_np[i].astype(np.float32), None,
+                                           **reference_port.FARNEBACK_PARAMS)
+        d = np.abs(flow[i] - ref).max(axis=2)
+        out["flow_max_px"] = max(out["flow_max_px"], float(d.max()))
+        out["flow_mean_px"] = max(out["flow_mean_px"], float(d.mean()))
+        out["flow_p999_px"] = max(out["flow_p999_px"], float(np.quantile(d, 0.999)))
+        rvx, rvy, _ = reference_port.compute_velocity_vectors(prev_np[i], next_np[i], xr, yr, 1.0)
+        m = reference_port.continuity_mask(rvx, rvy, ALPHA_CONT)
+        rvalid = np.sqrt((rvx * m) ** 2 + (rvy * m) ** 2) > 0.1
+        out["valid_cells_differing"] += int((rvalid != valid[i]).sum())
+        out["valid_cells"] += int(rvalid.sum())
+        n = int(min(n_valid[i], cap))
+        if n_valid[i] <= cap and n > 0:
+            want, widx = dbscan_np.dbscan_clustering_sklearn(vx_f[i].astype(np.float64), vy_f[i].astype(np.float64),
+                                                             valid[i], EPS, MIN_SAMPLES)
+            out["labels_identical"] &= bool(len(want) == n and np.array_equal(labels[i, :n], want))
+            out["indices_identical"] &= bool(len(widx) == n and np.array_equal(indices[i, :n], widx))
+            out["moving_cells_checked"] += n
+    out["what"] = ("GPU flow vs cv2 (max / mean / p99.9 |d| in px, worst pair); moving-cell mask vs the reference chain "
+                   "on cv2's flow (cells that flip sit within the flow tolerance of a threshold); labels and indices vs "
+                   "sklearn DBSCAN on the GPU's own vx_f, vy_f, valid")
+    return out
+
+
+def output_digest(eng, prev_d, next_d, params, px, py, cap):
+    """SHA-256 over everything one batch produces except the fp64 cluster sums: flow, filtered velocities,
+    valid mask, counts, labels and indices of the valid prefix."""
+    import hashlib
+    res = eng.flow_pipeline(prev_d, next_d, px, py, ALPHA_CONT, EPS, MIN_SAMPLES, params, cap=cap, max_clusters=0,
+                            keep_flow=True)
+    eng.synchronize()
+    h = hashlib.sha256()
+    for t in (res.flow, res.vx_f, res.vy_f, res.valid, res.n_valid, res.n_clusters):
+        h.update(t.cpu().numpy().tobytes())
+    nv = res.n_valid.cpu().numpy()
+    lab, idx = res.labels.cpu().numpy(), res.indices.cpu().numpy()
+    for b in range(len(nv)):
+        n = int(min(nv[b], cap))
+        h.update(lab[b, :n].tobytes())
+        h.update(idx[b, :n].tobytes())
+    return h.hexdigest()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -383,12 +485,46 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(te.item())
 
+    # ---- parity of what was just timed: every rank checks pairs of its own shard --------------------------
+    par = None
+    if not args.no_parity:
+        par = parity_block(eng, prev_h, next_h, params, px, py, args.cap, n_pairs=args.parity_pairs)
+    # ---- N > 1: shard outputs equal the single-GPU outputs bit for bit --------------------------------------
+    # every rank digests the outputs of the first pairs of its shard; rank 0 regenerates those pairs from
+    # their seeds, runs them on its own GPU and compares
+    n_eq = min(B, 8)
+    my_digest = output_digest(eng, prev_d[:n_eq], next_d[:n_eq], params, px, py, args.cap)
+    shard_equal = None
+    if world > 1:
+        digests = [None] * world
+        dist.all_gather_object(digests, my_digest)
+        if rank == 0:
+            same = []
+            for r in range(1, world):
+                ph, nh = synth.bev_pairs(r * n_pool, n_eq, H, W)
+                d0 = output_digest(eng, torch.from_numpy(ph).cuda(), torch.from_numpy(nh).cuda(), params, px, py, args.cap)
+                same.append(d0 == digests[r])
+            shard_equal = {"pairs_per_rank": n_eq, "ranks_checked": list(range(1, world)), "identical": bool(all(same)),
+                           "what": "SHA-256 of flow, vx_f, vy_f, valid, counts, labels, indices of each rank's first "
+                                   "pairs vs the same pairs recomputed on rank 0's GPU"}
+
     # ---- the only collective: gather per-shard metrics (off the hot path) -------------------------------
     shard = torch.tensor([n_valid_mean, n_clusters_mean, float(truncated)], dtype=torch.float64, device="cuda")
     if world > 1:
         gathered = [torch.empty_like(shard) for _ in range(world)]
         dist.all_gather(gathered, shard)
         shard_stats = torch.stack(gathered).cpu().numpy()
+        if par is not None:
+            pars = [None] * world
+            dist.all_gather_object(pars, par)
+            par = dict(par)
+            for k in ("flow_max_px", "flow_mean_px", "flow_p999_px"):
+                par[k] = max(q[k] for q in pars)
+            for k in ("valid_cells_differing", "valid_cells", "moving_cells_checked", "pairs"):
+                par[k] = sum(q[k] for q in pars)
+            for k in ("labels_identical", "indices_identical"):
+                par[k] = all(q[k] for q in pars)
+            par["ranks"] = world
     else:
         shard_stats = shard.cpu().numpy()[None]
 
@@ -425,6 +561,8 @@ def run_ours(args):
                          "whole_pipeline": {"A_bytes_per_pair": A, "achieved_gbs_per_gpu": whole,
                                             "frac": whole / peak}},
             "stage_ms_per_step": stage_ms,
+            "parity": par,
+            "shard_equality": shard_equal,
             "moving_cells_per_pair": float(shard_stats[:, 0].mean()),
             "clusters_per_pair": float(shard_stats[:, 1].mean()),
             "cap_truncated": bool(shard_stats[:, 2].any()),
@@ -432,11 +570,17 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             rounds = args.cpu_rounds
-            v, wall = cpu_pairs_per_sec(H, W, cores, rounds)
+            pool = cpu_pool(cores)      # imports and a tiny pass in every worker: start-up is not timed
+            try:
+                v, wall, stage = cpu_pairs_per_sec(H, W, cores, rounds, pool)
+            finally:
+                pool.close()
+                pool.join()
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{cores * rounds} pairs of the same workload ({cores} worker processes x "
-                                              f"{rounds}, cv2 single-threaded each), {wall:.1f} s wall, "
-                                              "oracle/reference_port.flow_to_clusters"}
+                                    "sample": f"{cores * rounds} pairs of the same workload ({cores} warm worker "
+                                              f"processes x {rounds}, cv2 single-threaded each), {wall:.1f} s wall, "
+                                              "the call sequence of oracle/reference_port.flow_to_clusters",
+                                    "stage_s_per_pair": {k: round(x, 4) for k, x in stage.items()}}
         print(json.dumps(line), flush=True)
     for e in engines:
         e.close()
@@ -458,6 +602,8 @@ def main():
     ap.add_argument("--max-clusters", type=int, default=1024)
     ap.add_argument("--cpu-rounds", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the cv2 / sklearn parity check of the timed workload")
+    ap.add_argument("--parity-pairs", type=int, default=2)
     ap.add_argument("--streams", type=int, default=1, help="engines (streams) per GPU that alternate over the steps")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -31,6 +31,16 @@ def farneback_params(**kw) -> _lib.FarnebackParams:
     return p
 
 
+def farneback_layers_host(H: int, W: int, params: dict | None = None):
+    """[(h, w)] of the pyramid layers the library processes, coarsest first (datmo_farneback_layers;
+    host-side arithmetic only, no device needed)."""
+    p = farneback_params(**{k: v for k, v in (params or {}).items()})
+    w = (C.c_int * 16)()
+    h = (C.c_int * 16)()
+    n = _lib.load().datmo_farneback_layers(H, W, C.byref(p), 16, w, h)
+    return [(h[i], w[i]) for i in range(n)]
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
