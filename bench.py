@@ -453,7 +453,8 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer API -------------------------------------------------------
     # pinned host uint8 pairs -> H2D -> flow..clusters -> D2H of counts / labels / indices / summaries,
-    # every batch; copies are double-buffered against compute (HostFlowPipeline).
+    # every batch, through the C-ABI chain object (HostFlowPipeline is its ctypes caller): copies on the
+    # library's own streams, double-buffered against the kernels.
     from datmo_using_optical_flow_b200.engine import HostFlowPipeline
     pipe = HostFlowPipeline(eng, B, H, W, px, py, ALPHA_CONT, EPS, MIN_SAMPLES, params, cap=args.cap,
                             max_clusters=args.max_clusters, n_slots=2)
@@ -480,6 +481,7 @@ def run_ours(args):
     barrier()
     e2e_wall = time.perf_counter() - t0
     h2d = pipe.h2d_bytes
+    pipe.close()
     te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -546,9 +548,9 @@ def run_ours(args):
             "config": workload_config(args, B),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(d2h_total / e2e_steps), "steps": e2e_steps,
-                    "what": "pinned host uint8 pairs -> H2D -> flow..clusters -> D2H of counts, labels (int32), "
-                            "indices (row << 16 | col, one int32 per moving cell), cluster summaries, every step; "
-                            "copies double-buffered against compute; wall clock"},
+                    "what": "the C-ABI chain (datmo_chain_submit / _collect): pinned host uint8 pairs -> H2D -> "
+                            "flow..clusters -> one D2H copy per array of counts, labels (int16), cell indices "
+                            "(row << 16 | col), cluster summaries, every step; two slots in flight; wall clock"},
             "gpu_launches": int(lc.item()),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_flow_iter_xm (updateMatrices + 15x15 box sums + 2x2 solve, fused)",

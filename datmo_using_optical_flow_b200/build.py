@@ -19,18 +19,31 @@ LIB_PATH = os.path.join(LIB_DIR, "libdatmo_b200.so")
 STAMP = os.path.join(LIB_DIR, "libdatmo_b200.stamp")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["context.cu", "farneback.cu", "velmask.cu", "dbscan.cu", "dbscan_runs.cu", "bev.cu", "ransac.cu"]
+SOURCES = ["context.cu", "farneback.cu", "velmask.cu", "dbscan.cu", "dbscan_runs.cu", "bev.cu", "ransac.cu", "chain.cu"]
 # files whose fp64 arithmetic must round every operation like numpy does (no FMA contraction)
 NO_FMAD = {"ransac.cu"}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE]
 
 
+class NvccMissing(RuntimeError):
+    """The sources changed (or the library is absent) and there is no nvcc to build it."""
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
             return cand
-    raise RuntimeError("nvcc not found: libdatmo_b200 cannot be built (there is no CPU fallback)")
+    raise NvccMissing("nvcc not found: libdatmo_b200 cannot be built (there is no CPU fallback)")
+
+
+def stamp_matches() -> bool:
+    """True when the built library's stamp equals the digest of the sources in this tree."""
+    try:
+        with open(STAMP) as fh:
+            return os.path.exists(LIB_PATH) and fh.read().strip() == _digest()
+    except OSError:
+        return False
 
 
 def _digest() -> str:

@@ -51,9 +51,22 @@ __device__ __forceinline__ void normal2(uint64_t seed, uint64_t ctr, double& n0,
     n1 = rad * s;
 }
 
-// Adds (count, value) for `cell` with one atomic per distinct cell in the warp.
+// Per-cell accumulator that does not depend on the order in which warps and CTAs arrive: a 128-bit
+// fixed-point sum (hi = integer part as int64, lo = fraction in units of 2^-64; see datmo_fixed_add in
+// common.cuh) plus an fp64 accumulator for non-finite input.  With fp64 atomicAdd the last bits of a
+// cell's mean changed from run to run, and with them — rarely — a uint8 of the grid.
+struct FixAcc {
+    unsigned long long* hi;
+    unsigned long long* lo;
+    double* ovf;
+};
+__device__ __forceinline__ double fix_value(const FixAcc& a, int i) {
+    return datmo_fixed_value(a.hi[i], a.lo[i], a.ovf[i]);
+}
+
+// Adds (count, value) for `cell` with one set of atomics per distinct cell in the warp.
 // Lanes with cell < 0 contribute nothing.  All 32 lanes must call.
-__device__ __forceinline__ void warp_scatter_add(int cell, double v, uint32_t* cnt, double* acc) {
+__device__ __forceinline__ void warp_scatter_add(int cell, double v, uint32_t* cnt, const FixAcc& acc) {
     const unsigned peers = __match_any_sync(0xffffffffu, cell);
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
@@ -70,7 +83,7 @@ __device__ __forceinline__ void warp_scatter_add(int cell, double v, uint32_t* c
     }
     if (lane == leader && cell >= 0) {
         if (cnt) atomicAdd(cnt + cell, static_cast<uint32_t>(__popc(peers)));
-        atomicAdd(acc + cell, sum);
+        datmo_fixed_add(acc.hi + cell, acc.lo + cell, reinterpret_cast<unsigned long long*>(acc.ovf + cell), sum);
     }
 }
 
@@ -88,8 +101,7 @@ __device__ __forceinline__ void load_point(const void* pts, int64_t i, double& x
 // pass 1 (PASS == 0): count and sum of z per cell; pass 2 (PASS == 1): sum of squared deviations
 template <int LAYOUT, int PASS>
 __global__ void __launch_bounds__(256) k_bev_accum(const void* __restrict__ pts, int64_t n, BevGeom g,
-                                                   uint32_t* __restrict__ cnt, double* __restrict__ sum,
-                                                   double* __restrict__ ssd) {
+                                                   uint32_t* __restrict__ cnt, FixAcc sum, FixAcc ssd) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t n_round = (n + 31) & ~int64_t(31);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
@@ -103,7 +115,7 @@ __global__ void __launch_bounds__(256) k_bev_accum(const void* __restrict__ pts,
                 if (PASS == 0) {
                     v = z;
                 } else {
-                    const double mean = __ddiv_rn(sum[cell], static_cast<double>(cnt[cell]));
+                    const double mean = __ddiv_rn(fix_value(sum, cell), static_cast<double>(cnt[cell]));
                     const double d = __dsub_rn(z, mean);
                     v = __dmul_rn(d, d);
                 }
@@ -121,8 +133,8 @@ __global__ void __launch_bounds__(256) k_pre_accum(const float4* __restrict__ pt
                                                    const uint8_t* __restrict__ ground, double rx0, double rx1,
                                                    double ry0, double ry1, double rz0, double rz1, int expansion,
                                                    double noise_std, const double* __restrict__ noise, uint64_t seed,
-                                                   BevGeom g, uint32_t* __restrict__ cnt, double* __restrict__ sum,
-                                                   double* __restrict__ ssd, unsigned long long* __restrict__ n_roi) {
+                                                   BevGeom g, uint32_t* __restrict__ cnt, FixAcc sum, FixAcc ssd,
+                                                   unsigned long long* __restrict__ n_roi) {
     const int64_t total = n * expansion;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t t_round = (total + 31) & ~int64_t(31);
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(256) k_pre_accum(const float4* __restrict__ pt
                     if (PASS == 0) {
                         v = z;
                     } else {
-                        const double mean = __ddiv_rn(sum[cell], static_cast<double>(cnt[cell]));
+                        const double mean = __ddiv_rn(fix_value(sum, cell), static_cast<double>(cnt[cell]));
                         const double d = __dsub_rn(z, mean);
                         v = __dmul_rn(d, d);
                     }
@@ -182,9 +194,9 @@ __device__ __forceinline__ double ord_to_double(unsigned long long u) {
     return __longlong_as_double(static_cast<long long>(u));
 }
 
-// per-cell value (a*mean + b*std)/h_max (main.py:116-118), written over `sum`; grid max
-__global__ void __launch_bounds__(256) k_bev_value(const uint32_t* __restrict__ cnt, double* __restrict__ sum,
-                                                   const double* __restrict__ ssd, int ncell, double a, double b,
+// per-cell value (a*mean + b*std)/h_max (main.py:116-118) -> val; grid max
+__global__ void __launch_bounds__(256) k_bev_value(const uint32_t* __restrict__ cnt, FixAcc sum, FixAcc ssd,
+                                                   double* __restrict__ val, int ncell, double a, double b,
                                                    double h_max, unsigned long long* __restrict__ gmax) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double v = 0.0;
@@ -192,11 +204,11 @@ __global__ void __launch_bounds__(256) k_bev_value(const uint32_t* __restrict__ 
         const uint32_t c = cnt[i];
         if (c > 0) {
             const double dn = static_cast<double>(c);
-            const double mean = __ddiv_rn(sum[i], dn);
-            const double sd = sqrt(__ddiv_rn(ssd[i], dn));
+            const double mean = __ddiv_rn(fix_value(sum, i), dn);
+            const double sd = sqrt(__ddiv_rn(fix_value(ssd, i), dn));
             v = __ddiv_rn(__dadd_rn(__dmul_rn(a, mean), __dmul_rn(b, sd)), h_max);
         }
-        sum[i] = v;
+        val[i] = v;
     }
     unsigned long long key = i < ncell ? ord_of(v) : 0ull;
 #pragma unroll
@@ -271,20 +283,28 @@ __global__ void __launch_bounds__(256) k_expand(const double* __restrict__ pts, 
 
 struct BevWs {
     uint32_t* cnt;
-    double* sum;
-    double* ssd;
+    FixAcc sum, ssd;
+    double* val;
     unsigned long long* gmax;
     unsigned long long* n_roi;
 };
 
+void bev_carve(Bump& bump, int ncell, BevWs& ws) {
+    ws.cnt = bump.take<uint32_t>(ncell);
+    for (FixAcc* a : {&ws.sum, &ws.ssd}) {
+        a->hi = bump.take<unsigned long long>(ncell);
+        a->lo = bump.take<unsigned long long>(ncell);
+        a->ovf = bump.take<double>(ncell);
+    }
+    ws.val = bump.take<double>(ncell);
+    ws.gmax = bump.take<unsigned long long>(2);
+    ws.n_roi = ws.gmax + 1;
+}
+
 int bev_ws(datmo_ctx* h, int ncell, BevWs& ws) {
     for (int pass = 0; pass < 2; ++pass) {
         Bump bump(pass ? h->ws : nullptr);
-        ws.cnt = bump.take<uint32_t>(ncell);
-        ws.sum = bump.take<double>(ncell);
-        ws.ssd = bump.take<double>(ncell);
-        ws.gmax = bump.take<unsigned long long>(2);
-        ws.n_roi = ws.gmax + 1;
+        bev_carve(bump, ncell, ws);
         if (!pass) DATMO_TRY(datmo_ws_reserve(h, bump.off));
         if (pass) DATMO_CHECK_CUDA(h, cudaMemsetAsync(h->ws, 0, bump.off, h->stream));
     }
@@ -294,12 +314,12 @@ int bev_ws(datmo_ctx* h, int ncell, BevWs& ws) {
 int bev_finish(datmo_ctx* h, const BevWs& ws, int ncell, double a, double b, double h_max, uint8_t* bev) {
     {
         LaunchScope ls(h, DATMO_TAG_BEV);
-        k_bev_value<<<ceil_div(ncell, 256), 256, 0, h->stream>>>(ws.cnt, ws.sum, ws.ssd, ncell, a, b, h_max, ws.gmax);
+        k_bev_value<<<ceil_div(ncell, 256), 256, 0, h->stream>>>(ws.cnt, ws.sum, ws.ssd, ws.val, ncell, a, b, h_max, ws.gmax);
     }
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, DATMO_TAG_BEV);
-        k_bev_norm<<<ceil_div(ncell, 256), 256, 0, h->stream>>>(ws.sum, ncell, ws.gmax, bev);
+        k_bev_norm<<<ceil_div(ncell, 256), 256, 0, h->stream>>>(ws.val, ncell, ws.gmax, bev);
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
@@ -376,8 +396,8 @@ int datmo_bev_rasterize_host(datmo_handle_t h, const void* pts, int layout, int6
     DATMO_TRY(check_geom(h, res_x, res_y, nx, ny));
     const size_t pbytes = static_cast<size_t>(n) * (layout == DATMO_PTS_F64_XYZ ? 24 : 16);
     const size_t ncell = static_cast<size_t>(nx) * ny;
-    char* d = nullptr;
-    DATMO_CHECK_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&d), pbytes + ncell + 512));
+    DATMO_TRY(datmo_io_reserve(h, pbytes + ncell + 512));
+    char* d = h->io;
     uint8_t* d_bev = reinterpret_cast<uint8_t*>(d + ((pbytes + 255) & ~size_t(255)));
     int st = DATMO_OK;
     cudaError_t e = cudaSuccess;
@@ -395,7 +415,6 @@ int datmo_bev_rasterize_host(datmo_handle_t h, const void* pts, int layout, int6
         h->err = cudaGetErrorString(e);
         st = DATMO_E_CUDA;
     }
-    cudaFree(d);
     return st;
 }
 
@@ -414,10 +433,8 @@ int datmo_preprocess_dev(datmo_handle_t h, const float* pts, int64_t n, int flip
     size_t bev_bytes;
     {
         Bump dry(nullptr);
-        dry.take<uint32_t>(ncell);
-        dry.take<double>(ncell);
-        dry.take<double>(ncell);
-        dry.take<unsigned long long>(2);
+        BevWs sizing;
+        bev_carve(dry, ncell, sizing);
         bev_bytes = dry.off;
     }
     const size_t mask_bytes = (static_cast<size_t>(n) + 255) & ~size_t(255);

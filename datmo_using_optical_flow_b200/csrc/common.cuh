@@ -12,6 +12,8 @@
 
 #include "../../include/datmo_b200.h"
 
+struct datmo_chain;
+
 struct datmo_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -23,6 +25,12 @@ struct datmo_ctx {
     // small pinned staging area for host-returning calls
     char* pinned = nullptr;
     size_t pinned_cap = 0;
+    // grow-only device staging of the "_host" entry points (inputs / outputs of a call; the workspace
+    // arena above belongs to the kernels)
+    char* io = nullptr;
+    size_t io_cap = 0;
+    // the chain datmo_flow_to_clusters_host keeps between calls with the same configuration
+    datmo_chain* chain_cache = nullptr;
     std::string err;
     // Farneback per-layer tables (pyramid taps, upsampling taps): cached on the device across calls
     // with the same geometry, so a steady-state call uploads nothing and never blocks the host
@@ -88,6 +96,7 @@ struct Bump {
 
 int datmo_ws_reserve(datmo_ctx* h, size_t bytes);
 int datmo_pinned_reserve(datmo_ctx* h, size_t bytes);
+int datmo_io_reserve(datmo_ctx* h, size_t bytes);
 
 // RAII-ish bracket around a kernel launch: counts it and, when profiling is on,
 // records an event pair on the handle's stream.
@@ -127,5 +136,33 @@ size_t datmo_dbscan_runs_workspace(int H, int W, int batch);
 int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy_f, const uint8_t* valid, int H, int W,
                       int batch, double eps, int min_samples, int cap, int32_t* n_valid, int32_t* labels,
                       int32_t* indices, int32_t* n_clusters, int (*tag)(int));
+
+#ifdef __CUDACC__
+// Order-independent accumulation of a partial sum p: p = hi + lo / 2^64 with hi = floor(p) (int64) and lo the
+// fraction as a 64-bit integer, added with two integer atomics (the low word's wrap-around carries into
+// the high one).  Integer addition commutes, so the total does not depend on the order in which warps
+// and CTAs arrive — unlike an fp64 atomicAdd, whose result changes in the last bits from run to run.
+// Bits of p below 2^-64 are dropped (the velocities are f32: nothing below 2^-40 of a value >= 2^-17
+// exists); a non-finite or astronomically large partial goes to an fp64 accumulator instead.
+__device__ __forceinline__ void datmo_fixed_add(unsigned long long* hi_acc, unsigned long long* lo_acc,
+                                          unsigned long long* overflow_acc, double p) {
+    if (!(fabs(p) < 4.0e18)) {
+        atomicAdd(reinterpret_cast<double*>(overflow_acc), p);
+        return;
+    }
+    const double fl = floor(p);
+    const long long hi = static_cast<long long>(fl);
+    const unsigned long long lo = __double2ull_rz((p - fl) * 18446744073709551616.0);
+    const unsigned long long old = atomicAdd(lo_acc, lo);
+    const unsigned long long carry = old + lo < old ? 1ull : 0ull;
+    atomicAdd(hi_acc, static_cast<unsigned long long>(hi) + carry);
+}
+
+// value of such an accumulator: (signed high word) + (low word) / 2^64 + the fp64 side accumulator
+__device__ __forceinline__ double datmo_fixed_value(unsigned long long hi, unsigned long long lo, double overflow) {
+    return static_cast<double>(static_cast<long long>(hi)) + static_cast<double>(lo) * 5.421010862427522e-20 + overflow;
+}
+
+#endif
 
 #define DATMO_POST_LAUNCH(h) DATMO_CHECK_CUDA(h, cudaGetLastError())

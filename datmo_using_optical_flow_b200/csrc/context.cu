@@ -25,6 +25,17 @@ int datmo_pinned_reserve(datmo_ctx* h, size_t bytes) {
     return DATMO_OK;
 }
 
+int datmo_io_reserve(datmo_ctx* h, size_t bytes) {
+    if (bytes <= h->io_cap) return DATMO_OK;
+    DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->io) DATMO_CHECK_CUDA(h, cudaFree(h->io));
+    h->io = nullptr;
+    h->io_cap = 0;
+    DATMO_CHECK_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->io), bytes));
+    h->io_cap = bytes;
+    return DATMO_OK;
+}
+
 LaunchScope::LaunchScope(datmo_ctx* h_, int tag, int n_launches) : h(h_) {
     h->launches += n_launches;
     if (!h->prof || !((h->prof_mask >> tag) & 1u)) return;
@@ -93,6 +104,7 @@ int datmo_destroy(datmo_handle_t h) {
     if (!h) return DATMO_E_INVALID;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->chain_cache) datmo_chain_destroy(h->chain_cache);
     for (auto& ev : h->ev_pool) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -100,6 +112,7 @@ int datmo_destroy(datmo_handle_t h) {
     if (h->ws) cudaFree(h->ws);
     if (h->fb_tab) cudaFree(h->fb_tab);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->io) cudaFree(h->io);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return DATMO_OK;

@@ -568,7 +568,8 @@ __global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__
                                                        int H, int W, int cap, const int32_t* __restrict__ n_valid,
                                                        const int32_t* __restrict__ labels,
                                                        const int32_t* __restrict__ indices, int max_clusters,
-                                                       unsigned long long* __restrict__ acc) {
+                                                       unsigned long long* __restrict__ acc,
+                                                       unsigned long long* __restrict__ extra) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const int n = min(n_valid[b], cap);
@@ -611,8 +612,9 @@ __global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__
         atomicAdd(a + 0, static_cast<unsigned long long>(lane - seg0 + 1));
         atomicAdd(a + 1, static_cast<unsigned long long>(sr));
         atomicAdd(a + 2, static_cast<unsigned long long>(sc));
-        atomicAdd(reinterpret_cast<double*>(a + 3), svx);
-        atomicAdd(reinterpret_cast<double*>(a + 4), svy);
+        unsigned long long* x = extra + (static_cast<size_t>(b) * max_clusters + lab) * 4;
+        datmo_fixed_add(a + 3, x + 0, x + 2, svx);
+        datmo_fixed_add(a + 4, x + 1, x + 3, svy);
         atomicAdd(a + 5, srr);
         atomicAdd(a + 6, src);
         atomicAdd(a + 7, scc);
@@ -620,13 +622,18 @@ __global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__
 }
 
 // in place: 64-bit accumulators -> the 8 doubles of the summary
-__global__ void __launch_bounds__(256) k_cluster_finalize(int total, unsigned long long* __restrict__ acc) {
+__global__ void __launch_bounds__(256) k_cluster_finalize(int total, unsigned long long* __restrict__ acc,
+                                                          const unsigned long long* __restrict__ extra) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     unsigned long long* a = acc + static_cast<size_t>(i) * 8;
+    const unsigned long long* x = extra + static_cast<size_t>(i) * 4;
     double* d = reinterpret_cast<double*>(a);
     const unsigned long long cnt = a[0];
     if (cnt == 0) return;  // all-zero bits are also 0.0
+    // sums of vx, vy: 128-bit fixed point + the fp64 accumulator for non-finite input
+    const double svx = datmo_fixed_value(a[3], x[0], __longlong_as_double(x[2]));
+    const double svy = datmo_fixed_value(a[4], x[1], __longlong_as_double(x[3]));
     const double n = static_cast<double>(cnt);
     const double sr = static_cast<double>(a[1]), sc = static_cast<double>(a[2]);
     const double srr = static_cast<double>(a[5]), src = static_cast<double>(a[6]), scc = static_cast<double>(a[7]);
@@ -639,8 +646,8 @@ __global__ void __launch_bounds__(256) k_cluster_finalize(int total, unsigned lo
     d[0] = n;
     d[1] = mr;
     d[2] = mc;
-    d[3] = d[3] / n;
-    d[4] = d[4] / n;
+    d[3] = svx / n;
+    d[4] = svy / n;
     d[5] = crr;
     d[6] = crc;
     d[7] = ccc;
@@ -751,18 +758,22 @@ extern "C" int datmo_cluster_summary_dev(datmo_handle_t h, const float* vx_f, co
     DATMO_REQUIRE(h, H >= 1 && W >= 1 && batch >= 1 && cap >= 1 && max_clusters >= 1, "bad sizes");
     DATMO_REQUIRE(h, batch <= 65535, "batch must fit a CUDA grid dimension");
     const size_t total = static_cast<size_t>(batch) * max_clusters;
+    // low words of the vx / vy sums and their overflow accumulators: 4 words per cluster in the workspace
+    DATMO_TRY(datmo_ws_reserve(h, total * 4 * sizeof(unsigned long long)));
+    unsigned long long* extra = reinterpret_cast<unsigned long long*>(h->ws);
     DATMO_CHECK_CUDA(h, cudaMemsetAsync(summary, 0, total * 8 * sizeof(double), h->stream));
+    DATMO_CHECK_CUDA(h, cudaMemsetAsync(extra, 0, total * 4 * sizeof(unsigned long long), h->stream));
     {
         LaunchScope ls(h, DATMO_TAG_CLUSTER);
         dim3 g(ceil_div(cap, 256), batch);
         k_cluster_accum<<<g, 256, 0, h->stream>>>(vx_f, vy_f, H, W, cap, n_valid, labels, indices, max_clusters,
-                                                  reinterpret_cast<unsigned long long*>(summary));
+                                                  reinterpret_cast<unsigned long long*>(summary), extra);
     }
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, DATMO_TAG_CLUSTER);
         k_cluster_finalize<<<ceil_div(static_cast<int>(total), 256), 256, 0, h->stream>>>(
-            static_cast<int>(total), reinterpret_cast<unsigned long long*>(summary));
+            static_cast<int>(total), reinterpret_cast<unsigned long long*>(summary), extra);
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;

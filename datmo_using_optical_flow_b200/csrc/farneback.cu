@@ -1890,8 +1890,8 @@ int datmo_farneback_host(datmo_handle_t h, const void* prev, const void* next, i
     const size_t N0 = static_cast<size_t>(H) * W;
     const size_t esz = dtype == DATMO_U8 ? 1 : 4;
     const size_t in_bytes = batch * N0 * esz, out_bytes = batch * N0 * 2 * sizeof(float);
-    char* d_io = nullptr;
-    DATMO_CHECK_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&d_io), 2 * in_bytes + out_bytes + 1024));
+    DATMO_TRY(datmo_io_reserve(h, 2 * in_bytes + out_bytes + 1024));   // grow-only: a steady stream of calls allocates once
+    char* d_io = h->io;
     char* d_prev = d_io;
     char* d_next = d_io + ((in_bytes + 255) & ~size_t(255));
     float* d_flow = reinterpret_cast<float*>(d_next + ((in_bytes + 255) & ~size_t(255)));
@@ -1913,7 +1913,6 @@ int datmo_farneback_host(datmo_handle_t h, const void* prev, const void* next, i
         h->err = cudaGetErrorString(e);
         st = DATMO_E_CUDA;
     }
-    cudaFree(d_io);
     return st;
 }
 

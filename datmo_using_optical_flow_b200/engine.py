@@ -452,110 +452,105 @@ def default_engine(device: int | None = None) -> Engine:
     return _default[dev]
 
 
-class HostFlowPipeline:
-    """Host-buffer entry to the flow -> clusters chain for a stream of frame-pair batches.
+def chain_config(H: int, W: int, batch: int, px_x: float, px_y: float, alpha_cont: float, eps: float,
+                 min_samples: int, cap: int, max_clusters: int = 1024, params=None, dtype=_lib.U8, thresh: float = 0.1,
+                 want_cells: bool = True, n_slots: int = 2) -> _lib.ChainConfig:
+    """datmo_chain_config with the reference's defaults filled in by the library."""
+    cfg = _lib.ChainConfig()
+    _lib.load().datmo_chain_default_config(C.byref(cfg))
+    cfg.H, cfg.W, cfg.batch, cfg.dtype = H, W, batch, dtype
+    cfg.px_x, cfg.px_y, cfg.alpha_cont, cfg.thresh = float(px_x), float(px_y), float(alpha_cont), float(thresh)
+    cfg.eps, cfg.min_samples = float(eps), int(min_samples)
+    cfg.cap, cfg.max_clusters, cfg.want_cells, cfg.n_slots = int(cap), int(max_clusters), int(want_cells), int(n_slots)
+    if params is not None:
+        cfg.fb = params
+    return cfg
 
-    Pinned host uint8 pairs go in, host arrays come out (counts, labels, indices, cluster
-    summaries — what the reference's driver loop consumes after main.py:577-615).  Copies
-    run on their own streams and are double-buffered against the compute stream, so batch
-    i+1 is uploading / computing while batch i is read back; every copy still happens for
-    every batch.  Usage: ``submit(slot, prev, nxt)`` then ``collect(slot)``; keep at most
-    ``n_slots`` submissions outstanding.
+
+class HostFlowPipeline:
+    """Host-buffer entry to the flow -> clusters chain for a stream of frame-pair batches: a thin
+    caller of the C-ABI chain object (datmo_chain_create / _submit / _collect, include/datmo_b200.h).
+
+    Host uint8 (or float32) pairs go in, host arrays come out (counts, labels, cell indices, cluster
+    summaries — what the reference's driver loop consumes after main.py:577-615).  The library
+    double-buffers the copies against the kernels on its own streams and reads every array back with
+    ONE device-to-host copy per batch.  Usage: ``submit(slot, prev, nxt)`` then ``collect(slot)``;
+    keep at most ``n_slots`` submissions outstanding.  Frames in pinned memory make the uploads
+    asynchronous.
     """
 
     def __init__(self, eng: Engine, batch: int, H: int, W: int, px_x: float, px_y: float, alpha_cont: float,
                  eps: float, min_samples: int, params=None, cap: int | None = None, max_clusters: int = 1024,
-                 n_slots: int = 2, packed_indices: bool | None = None):
+                 n_slots: int = 2, want_cells: bool = True, dtype=_lib.U8):
         self.eng, self.B, self.H, self.W = eng, batch, H, W
-        # (row << 16) | col in one int32 instead of an int32 pair: 8 instead of 12 bytes per moving cell
-        # over PCIe (with 8 GPUs on one host the read-back, not the GPUs, bounds the end-to-end rate)
-        self.packed = (H <= 65535 and W <= 65535) if packed_indices is None else bool(packed_indices)
-        self.args = (px_x, px_y, alpha_cont, eps, min_samples)
-        self.params = params or farneback_params()
-        self.cap = H * W if cap is None else cap
+        self.cap = H * W if cap is None else int(cap)
         self.max_clusters = max_clusters
-        with torch.cuda.device(eng.device):
-            self.h2d = torch.cuda.Stream(device=eng.device)
-            self.d2h = torch.cuda.Stream(device=eng.device)
-            self.flow_buf = eng.empty((batch, H, W, 2), torch.float32)
-            self.slots = []
-            for _ in range(n_slots):
-                self.slots.append(dict(
-                    prev=eng.empty((batch, H, W), torch.uint8), next=eng.empty((batch, H, W), torch.uint8),
-                    counts=torch.empty((2, batch), dtype=torch.int32).pin_memory(),
-                    labels=torch.empty((batch * self.cap,), dtype=torch.int32).pin_memory(),
-                    indices=torch.empty((batch * self.cap * (1 if self.packed else 2),), dtype=torch.int32).pin_memory(),
-                    summary=torch.empty((batch * max_clusters * 8,), dtype=torch.float64).pin_memory(),
-                    ev_h2d=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_d2h=torch.cuda.Event(),
-                    res=None, packed=None, busy=False))
-        self.h2d_bytes = 2 * batch * H * W
+        self.cfg = chain_config(H, W, batch, px_x, px_y, alpha_cont, eps, min_samples, self.cap, max_clusters, params,
+                                dtype=dtype, want_cells=want_cells, n_slots=n_slots)
+        c = C.c_void_p()
+        eng._check(eng.lib.datmo_chain_create(eng.h, C.byref(self.cfg), C.byref(c)))
+        self.c = c
+        self._held = [None] * n_slots     # the caller's frames stay alive until the slot is collected
+        self.h2d_bytes = 2 * batch * H * W * (1 if dtype == _lib.U8 else 4)
         self.d2h_bytes = 0
 
-    def submit(self, slot: int, prev_host: torch.Tensor, next_host: torch.Tensor):
-        s = self.slots[slot]
-        if s["busy"]:
-            raise RuntimeError("slot still in flight: collect() it first")
-        eng = self.eng
-        with torch.cuda.device(eng.device):
-            with torch.cuda.stream(self.h2d):
-                s["prev"].copy_(prev_host, non_blocking=True)
-                s["next"].copy_(next_host, non_blocking=True)
-                s["ev_h2d"].record(self.h2d)
-            eng.stream.wait_event(s["ev_h2d"])
-            px, py, alpha, eps, ms = self.args
-            res = eng.flow_pipeline(s["prev"], s["next"], px, py, alpha, eps, ms, self.params, cap=self.cap,
-                                    max_clusters=self.max_clusters, keep_flow=False, flow_buf=self.flow_buf)
-            s["packed"] = eng.pack_indices(res.indices, res.n_valid) if self.packed else None
-            with torch.cuda.stream(eng.stream):
-                s["counts"][0].copy_(res.n_valid, non_blocking=True)
-                s["counts"][1].copy_(res.n_clusters, non_blocking=True)
-                s["ev_done"].record(eng.stream)
-        s["res"] = res
-        s["busy"] = True
+    def close(self):
+        if getattr(self, "c", None) and getattr(self.eng, "h", None):
+            self.eng.lib.datmo_chain_destroy(self.c)
+        self.c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != _lib.OK:
+            raise _lib.DatmoError(st, self.eng.lib.datmo_chain_last_error(self.c).decode(errors="replace"))
+
+    @staticmethod
+    def _host_ptr(a):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda or not a.is_contiguous():
+                raise ValueError("frames must be contiguous host tensors")
+            return a.data_ptr()
+        a = np.ascontiguousarray(a)
+        return a.ctypes.data
+
+    def submit(self, slot: int, prev_host, next_host):
+        """prev_host / next_host: [B,H,W] host arrays (numpy or torch, ideally pinned)."""
+        self._held[slot] = (prev_host, next_host)
+        self._check(self.eng.lib.datmo_chain_submit(self.c, slot, C.c_void_p(self._host_ptr(prev_host)),
+                                                    C.c_void_p(self._host_ptr(next_host))))
 
     def collect(self, slot: int):
-        """-> (n_valid[B], n_clusters[B], offsets[B+1], labels[sum n], indices, summary[B,kmax,8])
-        numpy views into the slot's pinned buffers (valid until the slot is submitted again).  The labels /
-        indices of pair b are rows offsets[b]:offsets[b+1]; only the valid prefix of every pair crosses
-        the bus (one contiguous device-to-host copy per pair and array).  indices is [sum n] int32 holding
-        (row << 16) | col when the pipeline packs them (the default; ``unpack_indices`` gives [sum n, 2]),
-        else [sum n, 2] int32."""
-        s = self.slots[slot]
-        if not s["busy"]:
-            raise RuntimeError("nothing submitted on this slot")
-        s["ev_done"].synchronize()
-        counts = s["counts"].numpy()
-        nv = np.minimum(counts[0], self.cap).astype(np.int64)
-        offsets = np.zeros(self.B + 1, dtype=np.int64)
-        np.cumsum(nv, out=offsets[1:])
-        total = int(offsets[-1])
-        kmax = int(min(counts[1].max(), self.max_clusters))
-        res = s["res"]
+        """-> (n_valid[B], n_clusters[B], offsets[B+1], labels[sum n], cells[sum n], summary[B,kmax,8]):
+        numpy views into the chain's pinned buffers (valid until the slot is submitted again).  The cells of
+        pair b are rows offsets[b]:offsets[b+1].  labels is int16 when every pair of the batch has fewer than
+        32768 clusters, else int32; cells is uint32 (row << 16) | col (``unpack_indices`` gives [sum n, 2])."""
+        r = _lib.ChainResult()
+        self._check(self.eng.lib.datmo_chain_collect(self.c, slot, C.byref(r)))
+        self._held[slot] = None
         B = self.B
-        with torch.cuda.device(self.eng.device):
-            with torch.cuda.stream(self.d2h):
-                self.d2h.wait_event(s["ev_done"])
-                lab = s["labels"][:total]
-                idx = s["indices"][:total] if self.packed else s["indices"][:total * 2].view(total, 2)
-                src_idx = s["packed"] if self.packed else res.indices
-                summ = s["summary"][:B * kmax * 8].view(B, kmax, 8)
-                for b in range(B):
-                    n, o = int(nv[b]), int(offsets[b])
-                    if n:
-                        lab[o:o + n].copy_(res.labels[b, :n], non_blocking=True)
-                        idx[o:o + n].copy_(src_idx[b, :n], non_blocking=True)
-                if kmax:
-                    summ.copy_(res.summary[:, :kmax], non_blocking=True)
-                s["ev_d2h"].record(self.d2h)
-            s["ev_d2h"].synchronize()
-        self.d2h_bytes = counts.nbytes + lab.numel() * 4 + idx.numel() * 4 + summ.numel() * 8
-        s["res"] = None
-        s["packed"] = None
-        s["busy"] = False
-        return counts[0], counts[1], offsets, lab.numpy(), idx.numpy(), summ.numpy()
+        n_valid = np.ctypeslib.as_array(r.n_valid, shape=(B,))
+        n_clusters = np.ctypeslib.as_array(r.n_clusters, shape=(B,))
+        offsets = np.ctypeslib.as_array(r.offsets, shape=(B + 1,))
+        total = int(offsets[B])
+        if r.labels and total:
+            lt = C.c_int16 if r.label_bytes == 2 else C.c_int32
+            labels = np.ctypeslib.as_array(C.cast(r.labels, C.POINTER(lt)), shape=(total,))
+            cells = np.ctypeslib.as_array(r.cells, shape=(total,))
+        else:
+            labels, cells = np.zeros(0, np.int16), np.zeros(0, np.uint32)
+        k = r.summary_rows
+        summary = np.ctypeslib.as_array(r.summary, shape=(B, k, 8)) if k else np.zeros((B, 0, 8))
+        self.d2h_bytes = int(r.d2h_bytes)
+        self.truncated = bool(r.truncated)
+        return n_valid, n_clusters, offsets, labels, cells, summary
 
     @staticmethod
     def unpack_indices(packed: np.ndarray) -> np.ndarray:
-        """[n] int32 (row << 16) | col -> [n, 2] int32 (row, col), as dbscan_clustering's valid_indices."""
+        """[n] (row << 16) | col -> [n, 2] int32 (row, col), as dbscan_clustering's valid_indices."""
         u = packed.view(np.uint32)
         return np.stack([(u >> 16).astype(np.int32), (u & 0xffff).astype(np.int32)], axis=1)

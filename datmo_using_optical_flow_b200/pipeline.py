@@ -74,7 +74,10 @@ def process_clouds(clouds, config=None, engine=None, seed=0, ground_masks=None, 
                 labels, indices, clusters = out[:3]
                 if len(labels) == 0:
                     raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by DBSCAN.")
-                tm.update(clusters, cfg["dt"])
+                # main.py:618-634: association + EKF, THEN the savers, THEN lifetimes and manage_tracks — a
+                # confirmed track that manage_tracks deletes on this pair is still in this pair's files
+                tm.associate_and_update(clusters, cfg["dt"])
+                saved_tracks = tm.as_array()
                 if output_dir is not None:
                     k = i - 1
                     if save_grids:
@@ -87,8 +90,9 @@ def process_clouds(clouds, config=None, engine=None, seed=0, ground_masks=None, 
                     artefacts.save_dbscan_results(output_dir, labels, indices, k)
                     artefacts.save_ekf_tracks(output_dir, tm, k)
                     artefacts.save_all_velocities_to_csv(tm, k, tracks_csv)
+                tm.step_lifetimes()
                 rec = dict(index=i - 1, skipped=False, labels=labels, indices=indices, clusters=clusters,
-                           tracks=tm.as_array())
+                           tracks=tm.as_array(), saved_tracks=saved_tracks)
             except Exception as exc:
                 if verbose:
                     print(f"Error processing frames {i - 1} and {i}: {exc}")

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DATMO_ABI_VERSION 1
+#define DATMO_ABI_VERSION 2
 
 #define DATMO_OK 0
 #define DATMO_E_INVALID -1   /* bad argument */
@@ -241,6 +241,69 @@ int datmo_preprocess_dev(datmo_handle_t h, const float* pts, int64_t n, int flip
                          const uint8_t* ground_mask, const double roi[6], int expansion,
                          double noise_std, const double* noise, double res_x, double res_y, double x_lo,
                          double y_lo, int nx, int ny, double h_max, uint8_t* bev, int64_t* n_roi);
+
+/* ---- flow -> clusters for batches of frame pairs in HOST memory ------------------------
+ * The body of process_multiple_frames between the two BEVs and the EKF, main.py:577-615:
+ * compute_velocity_vectors (main.py:131-164), continuity_mask (main.py:224-228), the inline
+ * moving-cell filter (main.py:596-609), dbscan_clustering (main.py:231-259) and
+ * extract_cluster_data (main.py:402-434), for `batch` frame pairs per submission.
+ *
+ * A chain is a pipelined object on top of a handle: datmo_chain_submit enqueues the
+ * host-to-device copy of one batch (on a copy stream), the kernels (on the handle's stream) and a
+ * gather of the ragged per-pair results into one contiguous buffer per array, and returns without
+ * blocking; datmo_chain_collect waits for the batch and reads it back with ONE device-to-host copy
+ * per array (labels, cells, summaries), sized from the batch's own counts.  With n_slots >= 2 the
+ * copies of one batch overlap the kernels of the next.  Frames in pinned (page-locked) host memory
+ * make the uploads asynchronous; pageable memory works and is staged by the driver. */
+typedef struct datmo_chain_config {
+    int H, W, batch;         /* frame geometry; pairs per submission */
+    int dtype;               /* DATMO_U8 or DATMO_F32 frames */
+    double px_x, px_y;       /* metres per pixel: range / shape, main.py:147-150 */
+    double alpha_cont;       /* config.yaml masks.alpha_cont[0] */
+    double thresh;           /* moving-cell threshold, 0.1 at main.py:609 */
+    double eps;              /* config.yaml dbscan_params */
+    int min_samples;
+    int cap;                 /* moving cells kept per pair (row-major prefix; counts are exact) */
+    int max_clusters;        /* summary rows per pair; 0 = no summaries */
+    int want_cells;          /* 1: label + cell index of every moving cell come back; 0: counts, summaries */
+    int n_slots;             /* submissions that may be in flight, 1..16 */
+    datmo_farneback_params fb;
+} datmo_chain_config;
+
+/* Results of one submission.  Pointers are into pinned host memory owned by the chain and stay valid
+ * until the slot is submitted again.  The cells of pair b are entries offsets[b] .. offsets[b+1]-1 of
+ * labels / cells, in row-major order of the moving cells (np.nonzero order). */
+typedef struct datmo_chain_result {
+    const int32_t* n_valid;     /* [batch] moving cells per pair (may exceed cap) */
+    const int32_t* n_clusters;  /* [batch] */
+    const int64_t* offsets;     /* [batch + 1] */
+    const void* labels;         /* int16 when label_bytes == 2 (every pair has < 32768 clusters), else int32; -1 = noise */
+    int label_bytes;
+    const uint32_t* cells;      /* (row << 16) | col */
+    const double* summary;      /* [batch][summary_rows][8]: count, mean row, mean col, mean vx, mean vy, cov rr, rc, cc */
+    int summary_rows;           /* min(max over pairs of n_clusters, max_clusters) */
+    int truncated;              /* some pair had more than cap moving cells */
+    int64_t h2d_bytes, d2h_bytes; /* bytes this submission moved over the bus */
+} datmo_chain_result;
+
+typedef struct datmo_chain* datmo_chain_t;
+/* reference defaults: alpha_cont 0.2, thresh 0.1, eps 5, min_samples 3, Farneback of main.py:132-140;
+ * H, W, px_x, px_y, cap must be set by the caller */
+void datmo_chain_default_config(datmo_chain_config* cfg);
+int datmo_chain_create(datmo_handle_t h, const datmo_chain_config* cfg, datmo_chain_t* out);
+int datmo_chain_destroy(datmo_chain_t c);
+const char* datmo_chain_last_error(datmo_chain_t c);
+/* prev / next: [batch][H][W] of cfg.dtype in host memory; must stay untouched until the slot is collected */
+int datmo_chain_submit(datmo_chain_t c, int slot, const void* prev_host, const void* next_host);
+int datmo_chain_collect(datmo_chain_t c, int slot, datmo_chain_result* out);
+/* One-shot form with caller-owned outputs (the chain is cached on the handle between calls with the
+ * same configuration; cfg->n_slots and cfg->want_cells are ignored).  labels int32 [capacity_cells],
+ * indices int32 [capacity_cells][2] (row, col) — either may be NULL; summary double
+ * [batch][max_clusters][8] or NULL; offsets int64 [batch + 1].  Returns DATMO_E_CAPACITY when the
+ * cells do not fit capacity_cells or a pair exceeded cfg->cap (counts and offsets are still written). */
+int datmo_flow_to_clusters_host(datmo_handle_t h, const void* prev, const void* next, const datmo_chain_config* cfg,
+                                int32_t* n_valid, int32_t* n_clusters, int64_t* offsets, int32_t* labels,
+                                int32_t* indices, int64_t capacity_cells, double* summary);
 
 #ifdef __cplusplus
 }

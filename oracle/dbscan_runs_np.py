@@ -16,10 +16,17 @@ can be pinned against live sklearn (the library the reference calls at
               neighbour pair if some |xa - xb| <= rp[dr], rp[dr] = max dc with
               dr^2 + dc^2 <= eps^2
   responsible the first cell of A that sees B in its window: the head of A for every
-              run already in the head's window, otherwise the cell at b0 - rp[dr]
+              run already in the head's window, otherwise the cell at b0 - rp[dr].  Only heads
+              do work: A's head looks up at the runs in its window; B's head looks DOWN at the
+              one run that covers its window's left edge from further left (that run's first
+              cell to see B is b0 - rp[dr])
   pair work   skip when both heads already share a root; else test the cell pairs of
               (A, B) until one is within eps, then union
-Passes: rows dr = 0..1 first, then dr = 2..floor(eps) (after a flatten in the kernel).
+  passes      1: every head points at the run above its first vertical link (core cell whose
+              upper neighbour is core and within eps) inside the head's own 32-cell word — no
+              atomics; 2 (after a flatten): all pairs within reach, rows 0..floor(eps) above,
+              except that a pair two or more rows apart is dropped when an unbroken column of
+              vertical links joins the two runs (the row-1 pairs along it make the union).
 """
 from __future__ import annotations
 
@@ -145,27 +152,58 @@ def dbscan_runs(vx_filtered, vy_filtered, valid_mask, eps=1.0, min_samples=5, st
                     return
 
     core_cells = np.array(np.nonzero(core)).T.tolist()
-    for dr_lo, dr_hi in ((0, min(1, r)), (2, r)):
-        for y, x in core_cells:
-            for dr in range(dr_lo, dr_hi + 1):
-                yy = y - dr
-                if yy < 0:
-                    continue
-                w = rp[dr]
-                if head[y, x]:
-                    c_lo, c_hi = x - w, (x + w if dr > 0 else x - 1)
-                    first = True
-                    for c in range(c_lo, c_hi + 1):
-                        if c < 0 or c >= W:
-                            first = True   # window clipped by the image edge: the next core cell starts a run
-                            continue
-                        if core[yy, c] and (first or head[yy, c]):
+    # vertical links: a core cell whose upper neighbour is core and within eps
+    up = np.zeros((H, W), dtype=bool)
+    for y, x in core_cells:
+        if y > 0 and core[y - 1, x] and within(y, x, y - 1, x):
+            up[y, x] = True
+
+    def word_part(y, a0):
+        """cells of the run headed at (y, a0) that lie in the head's own 32-cell word"""
+        return range(a0, min(run_end(y, a0), (a0 // 32) * 32 + 31) + 1)
+
+    # pass 1 (no atomics in the kernel): every head points at the run above its first vertical link
+    for y, a0 in np.array(np.nonzero(head)).T.tolist():
+        for x in word_part(y, a0):
+            if up[y, x]:
+                parent[y * W + a0] = (y - 1) * W + head_of(y - 1, x)
+                counters["unions"] += 1
+                break
+    # pass 2: every pair of runs within reach, rows 0 .. r above.  Rows >= 2 above: the run reached
+    # from the head's word part through an unbroken column of vertical links is joined by the row-1
+    # pairs along that column, so the pair is dropped without a look at the forest.
+    for y, x in core_cells:
+        if not head[y, x]:
+            continue
+        for dr in range(0, r + 1):
+            yy = y - dr
+            w = rp[dr]
+            # looking down: the run of row y + dr that covers the window's left edge with its head further
+            # left does not see this head's run from ITS head; its first cell that does is x - w
+            yd = y + dr
+            if dr > 0 and yd < H and x - w >= 0 and core[yd, x - w] and not head[yd, x - w]:
+                process(yd, x - w, y, x)
+            if yy < 0:
+                continue
+            if True:
+                implied = -1
+                if dr >= 2:
+                    for xc in word_part(y, x):
+                        if all(up[y - i, xc] for i in range(dr)):
+                            implied = head_of(yy, xc)
+                            break
+                c_lo, c_hi = x - w, (x + w if dr > 0 else x - 1)
+                first = True
+                for c in range(c_lo, c_hi + 1):
+                    if c < 0 or c >= W:
+                        first = True   # window clipped by the image edge: the next core cell starts a run
+                        continue
+                    if core[yy, c] and (first or head[yy, c]):
+                        if implied >= 0 and head_of(yy, c) == implied:
+                            counters["skipped"] += 1
+                        else:
                             process(y, x, yy, c)
-                        first = not core[yy, c]
-                elif dr > 0:
-                    c = x + w
-                    if c < W and head[yy, c]:
-                        process(y, x, yy, c)
+                    first = not core[yy, c]
     # labels
     root = -np.ones((H, W), dtype=np.int64)
     for y, x in core_cells:

@@ -181,6 +181,10 @@ def tracker_golden():
             eig = np.abs(rng.normal(0.05, 0.02, 2)) if j < 3 else np.abs(rng.normal(4.0, 1.0, 2))
             cl[k] = dict(centroid=c, measurement=[c[0], c[1], vels[j][0], vels[j][1]], eigenvalues=eig)
             k += 1
+        # a parked object seen on every pair: its track is matched every time, gets confirmed, and
+        # manage_tracks deletes it once its lifetime passes N2 = 15 (main.py:505-507)
+        c = np.array([100.0, 60.0]) + rng.normal(0, 0.01, 2)
+        cl[k] = dict(centroid=c, measurement=[c[0], c[1], 0.0, 0.0], eigenvalues=np.abs(rng.normal(0.02, 0.005, 2)))
         frames.append(cl)
     tracks, lifetimes, confirmed = {}, {}, set()
     out = {"versions": versions(), "n_frames": np.array(len(frames))}
@@ -190,6 +194,10 @@ def tracker_golden():
         out[f"f{f}_meas"] = np.array([cl[k]["measurement"] for k in keys]).reshape(-1, 4)
         out[f"f{f}_eig"] = np.array([cl[k]["eigenvalues"] for k in keys]).reshape(-1, 2)
         tracks = ref.track_clusters(tracks, cl, 1.0, np.eye(4) * 0.1, np.eye(4) * 0.05, gamma=0.5)
+        # what save_ekf_tracks / save_all_velocities_to_csv see (main.py:619-620): the table BEFORE the
+        # lifetime update and manage_tracks
+        out[f"f{f}_saved"] = np.array([[tid, *tracks[tid].state.tolist()] for tid in tracks],
+                                      dtype=np.float64).reshape(-1, 5)
         for tid in list(lifetimes.keys()):
             if tid in tracks:
                 lifetimes[tid] += 1

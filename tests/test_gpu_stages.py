@@ -330,8 +330,11 @@ def test_preprocess_with_device_ransac_and_device_noise(engine):
     assert bev is not None and bev.shape == (400, 400) and bev.dtype == np.uint8 and bev.max() == 255
     occ = (bev > 0).mean()
     assert 0.001 < occ < 0.2        # ground removed: only objects remain
-    bev2 = main.preprocess_points(pts, c["grid_resolution"], c["x_range"], c["y_range"], 2.0, roi, seed=3, engine=engine)
-    assert (bev != bev2).mean() < 1e-3     # same seed -> same noise; atomics may flip a last bit, never more
+    # same seed -> same hypotheses, same noise, and accumulators that do not depend on the order in which the
+    # warps arrive (128-bit fixed-point sums): the grid is reproducible bit for bit
+    for _ in range(3):
+        bev2 = main.preprocess_points(pts, c["grid_resolution"], c["x_range"], c["y_range"], 2.0, roi, seed=3, engine=engine)
+        assert np.array_equal(bev, bev2)
     # empty ROI -> None, like the reference (main.py:84-86)
     assert main.preprocess_points(pts, c["grid_resolution"], c["x_range"], c["y_range"], 2.0,
                                   [1000, 1001, 1000, 1001, 0, 1], engine=engine) is None
@@ -386,34 +389,42 @@ def test_sequence_pipeline_tracks_the_mover(engine, tmp_path):
     assert (tmp_path / "filtered_velocities.csv").read_text().startswith("Frame Index,Point Index,Filtered X Velocity")
 
 
-@pytest.mark.parametrize("packed", [True, False])
-def test_host_flow_pipeline_matches_device_chain(engine, packed):
-    """The host-buffer entry (bench.py's e2e leg): pinned uint8 in, ragged labels / indices / summaries out,
-    with and without the packed (row << 16 | col) read-back, against the device-resident chain."""
+@pytest.mark.parametrize("want_cells", [True, False])
+def test_host_flow_pipeline_matches_device_chain(engine, want_cells):
+    """The host-buffer entry (bench.py's e2e leg, a thin caller of the C-ABI chain): pinned uint8 in, compact
+    labels (int16) / packed cell indices / summaries out — or counts and summaries only — against the
+    device-resident chain, three double-buffered batches."""
     from datmo_using_optical_flow_b200.engine import HostFlowPipeline, farneback_params
     B, H, W = 3, 200, 240
     pipe = HostFlowPipeline(engine, B, H, W, 0.25, 0.25, 0.2, 5.0, 3, farneback_params(), cap=H * W, max_clusters=256,
-                            packed_indices=packed)
+                            want_cells=want_cells)
     batches = [synth.bev_pairs(10 * k, B, H, W) for k in range(3)]
     pins = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in batches]
     outs = []
     pipe.submit(0, *pins[0])
+    with pytest.raises(Exception):
+        pipe.submit(0, *pins[0])          # the slot is in flight
     for k in range(3):
         if k + 1 < 3:
             pipe.submit((k + 1) % 2, *pins[k + 1])
         nv, ncl, off, lab, idx, summ = pipe.collect(k % 2)
-        outs.append((nv.copy(), ncl.copy(), off.copy(), lab.copy(),
-                     (HostFlowPipeline.unpack_indices(idx) if packed else idx).copy(), summ.copy()))
-    assert pipe.d2h_bytes > 0
+        outs.append((nv.copy(), ncl.copy(), off.copy(), lab.copy(), HostFlowPipeline.unpack_indices(idx).copy(), summ.copy()))
+    assert pipe.d2h_bytes > 0 and not pipe.truncated
     for k, (a, b) in enumerate(batches):
         res = engine.flow_pipeline(dev(a), dev(b), 0.25, 0.25, 0.2, 5.0, 3, farneback_params(), cap=H * W,
                                    max_clusters=256)
         nv, ncl, off, lab, idx, summ = outs[k]
         assert np.array_equal(nv, host(res.n_valid)) and np.array_equal(ncl, host(res.n_clusters))
-        for i in range(B):
-            n = int(nv[i])
-            assert np.array_equal(lab[off[i]:off[i] + n], host(res.labels)[i, :n])
-            assert np.array_equal(idx[off[i]:off[i] + n], host(res.indices)[i, :n])
+        assert np.array_equal(np.diff(off), nv)
+        if want_cells:
+            assert lab.dtype == np.int16
+            for i in range(B):
+                n = int(nv[i])
+                assert np.array_equal(lab[off[i]:off[i] + n], host(res.labels)[i, :n])
+                assert np.array_equal(idx[off[i]:off[i] + n], host(res.indices)[i, :n])
+        else:
+            assert len(lab) == 0
         kmax = summ.shape[1]
-        # mean vx / vy come from fp64 atomics (summation order varies run to run); the rest is exact
-        assert np.allclose(summ, host(res.summary)[:, :kmax], rtol=1e-12, atol=1e-15, equal_nan=True)
+        assert kmax == int(ncl.max())
+        assert np.array_equal(summ, host(res.summary)[:, :kmax], equal_nan=True)
+    pipe.close()

@@ -21,15 +21,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_tracker_matches_reference_golden(golden):
     g = golden("tracks.npz")
     tm = TrackManager()
+    deleted_now = 0
     for f in range(int(g["n_frames"])):
         cen, meas, eig = g[f"f{f}_centroid"], g[f"f{f}_meas"], g[f"f{f}_eig"]
         clusters = {k: dict(centroid=cen[k], measurement=meas[k].tolist(), eigenvalues=eig[k]) for k in range(len(cen))}
-        tm.update(clusters, 1.0)
+        # the two halves of the reference's loop body (main.py:618 | 621-634) with the savers in between
+        tm.associate_and_update(clusters, 1.0)
+        saved = g[f"f{f}_saved"]      # what save_ekf_tracks / the tracks CSV hold for this pair (main.py:619-620)
+        got_saved = np.array([[tid, *t.state.tolist()] for tid, t in tm.tracks.items()], dtype=np.float64).reshape(-1, 5)
+        assert got_saved.shape == saved.shape, f
+        np.testing.assert_allclose(got_saved, saved, rtol=1e-12, atol=1e-12, err_msg=f"saved, frame {f}")
+        deleted_now += len(saved) - len(g[f"f{f}_tracks"])
+        tm.step_lifetimes()
         want = g[f"f{f}_tracks"]
         got = tm.as_array()
         assert got.shape == want.shape, f
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, err_msg=f"frame {f}")
     assert len(tm.confirmed) >= 1
+    # the stream is long enough for manage_tracks to delete a confirmed track (lifetime 16..25): on that pair
+    # the saved table still holds it, the post-manage table does not
+    assert int(g["n_frames"]) >= 17 and deleted_now >= 1
 
 
 def test_tracker_reference_quirks():
