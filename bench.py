@@ -269,16 +269,21 @@ def parity_block(eng, prev_np, next_np, params, px, py, cap, n_pairs=2):
     valid = res.valid.cpu().numpy().astype(bool)
     n_valid = res.n_valid.cpu().numpy()
     labels, indices = res.labels.cpu().numpy(), res.indices.cpu().numpy()
-    out = dict(pairs=n_pairs, flow_max_px=0.0, flow_mean_px=0.0, flow_p999_px=0.0, valid_cells_differing=0,
+    from oracle import flow_stability
+    out = dict(pairs=n_pairs, flow_max_px=0.0, flow_mean_px=0.0, flow_p999_px=0.0, flow_max_px_stable=0.0,
+               flow_mean_px_stable=0.0, stable_fraction=1.0, cv2_self_max_px=0.0, valid_cells_differing=0,
                valid_cells=0, labels_identical=True, indices_identical=True, moving_cells_checked=0)
     xr, yr = [-0.5 * px * W, 0.5 * px * W], [-0.5 * py * H, 0.5 * py * H]
     for i in range(n_pairs):
-        ref = cv2.calcOpticalFlowFarneback(prev_np[i].astype(np.float32), next_np[i].astype(np.float32), None,
-                                           **reference_port.FARNEBACK_PARAMS)
-        d = np.abs(flow[i] - ref).max(axis=2)
-        out["flow_max_px"] = max(out["flow_max_px"], float(d.max()))
-        out["flow_mean_px"] = max(out["flow_mean_px"], float(d.mean()))
-        out["flow_p999_px"] = max(out["flow_p999_px"], float(np.quantile(d, 0.999)))
+        # whole frame, and the pixels where cv2 itself is stable under a 1-ulp input perturbation
+        r = flow_stability.compare(flow[i], prev_np[i], next_np[i], reference_port.FARNEBACK_PARAMS)
+        out["flow_max_px"] = max(out["flow_max_px"], r["max_all"])
+        out["flow_mean_px"] = max(out["flow_mean_px"], r["mean_all"])
+        out["flow_p999_px"] = max(out["flow_p999_px"], r["p999_all"])
+        out["flow_max_px_stable"] = max(out["flow_max_px_stable"], r["max_stable"])
+        out["flow_mean_px_stable"] = max(out["flow_mean_px_stable"], r["mean_stable"])
+        out["stable_fraction"] = min(out["stable_fraction"], r["stable_fraction"])
+        out["cv2_self_max_px"] = max(out["cv2_self_max_px"], r["ref_self_max"])
         rvx, rvy, _ = reference_port.compute_velocity_vectors(prev_np[i], next_np[i], xr, yr, 1.0)
         m = reference_port.continuity_mask(rvx, rvy, ALPHA_CONT)
         rvalid = np.sqrt((rvx * m) ** 2 + (rvy * m) ** 2) > 0.1
@@ -291,9 +296,11 @@ def parity_block(eng, prev_np, next_np, params, px, py, cap, n_pairs=2):
             out["labels_identical"] &= bool(len(want) == n and np.array_equal(labels[i, :n], want))
             out["indices_identical"] &= bool(len(widx) == n and np.array_equal(indices[i, :n], widx))
             out["moving_cells_checked"] += n
-    out["what"] = ("GPU flow vs cv2 (max / mean / p99.9 |d| in px, worst pair); moving-cell mask vs the reference chain "
-                   "on cv2's flow (cells that flip sit within the flow tolerance of a threshold); labels and indices vs "
-                   "sklearn DBSCAN on the GPU's own vx_f, vy_f, valid")
+    out["what"] = ("GPU flow vs cv2, worst pair: max / mean / p99.9 |d| in px over the whole frame, and max / mean over "
+                   "the pixels where cv2's own flow moves by <= 1e-4 px when its input is perturbed by one float32 ulp "
+                   "(stable_fraction of the frame; cv2_self_max_px is how far cv2 moves elsewhere); moving-cell mask vs "
+                   "the reference chain on cv2's flow (cells that flip sit within the flow tolerance of a threshold); "
+                   "labels and indices vs sklearn DBSCAN on the GPU's own vx_f, vy_f, valid")
     return out
 
 
@@ -520,8 +527,10 @@ def run_ours(args):
             pars = [None] * world
             dist.all_gather_object(pars, par)
             par = dict(par)
-            for k in ("flow_max_px", "flow_mean_px", "flow_p999_px"):
+            for k in ("flow_max_px", "flow_mean_px", "flow_p999_px", "flow_max_px_stable", "flow_mean_px_stable",
+                      "cv2_self_max_px"):
                 par[k] = max(q[k] for q in pars)
+            par["stable_fraction"] = min(q["stable_fraction"] for q in pars)
             for k in ("valid_cells_differing", "valid_cells", "moving_cells_checked", "pairs"):
                 par[k] = sum(q[k] for q in pars)
             for k in ("labels_identical", "indices_identical"):

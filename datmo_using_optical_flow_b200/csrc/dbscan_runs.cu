@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(128) k_run_pairs(const float* __restrict__ vx,
                                                    const uint32_t* __restrict__ hbits,
                                                    const uint32_t* __restrict__ ubits, RunGeom g, EpsTest eps2,
                                                    const int32_t* __restrict__ hlist, int hcap,
-                                                   const int32_t* __restrict__ hcount, int dr_max,
+                                                   const int32_t* __restrict__ hcount, int dr_min, int dr_max,
                                                    int32_t* __restrict__ parent) {
     const int b = blockIdx.y;
     const int n = min(hcount[b], hcap);
@@ -570,7 +570,8 @@ __global__ void __launch_bounds__(128) k_run_pairs(const float* __restrict__ vx,
                 else
                     run_pair(g, eps2, vxi, vyi, cimg, himg, par, ya, xa, yb, xb, a0, b0, pend);
             };
-            for (int d0 = 0; d0 <= dr_max; d0 += PAIR_ROWS) {
+            if (dr_min > 0) chain = uimg[static_cast<size_t>(y) * g.Ww + w];   // rows y .. y - dr_min + 1 (dr_min <= 1)
+            for (int d0 = dr_min; d0 <= dr_max; d0 += PAIR_ROWS) {
                 W3 ht[PAIR_ROWS], ct[PAIR_ROWS];
                 uint32_t ut[PAIR_ROWS], cd[PAIR_ROWS], hdn[PAIR_ROWS];
 #pragma unroll
@@ -867,7 +868,7 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
     // 260 000-cell frame)
     {
         LaunchScope ls(h, tag(4));
-        k_run_pairs<<<grid_list, 128, 0, s>>>(vx_f, vy_f, cbits, hbits, ubits, g, eps2, hlist, hcap, hcount, 0, parent);
+        k_run_pairs<<<grid_list, 128, 0, s>>>(vx_f, vy_f, cbits, hbits, ubits, g, eps2, hlist, hcap, hcount, 0, 0, parent);
     }
     DATMO_POST_LAUNCH(h);
     {
@@ -877,7 +878,7 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, tag(4));
-        k_run_pairs<<<grid_list, 128, 0, s>>>(vx_f, vy_f, cbits, hbits, ubits, g, eps2, hlist, hcap, hcount, g.r, parent);
+        k_run_pairs<<<grid_list, 128, 0, s>>>(vx_f, vy_f, cbits, hbits, ubits, g, eps2, hlist, hcap, hcount, 1, g.r, parent);
     }
     DATMO_POST_LAUNCH(h);
     {

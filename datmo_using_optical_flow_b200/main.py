@@ -24,7 +24,7 @@ from .engine import Engine, default_engine, farneback_params
 __all__ = ["filter_points_in_roi", "increase_point_density", "compute_bev_grid", "preprocess_points",
            "preprocess_pcd", "compute_velocity_vectors", "continuity_mask", "propagation_mask",
            "propagation_mask_with_acceleration", "moving_cell_filter",
-           "dbscan_clustering", "extract_cluster_data", "flow_to_clusters", "read_pcd"]
+           "dbscan_clustering", "extract_cluster_data", "clusters_from_summary", "flow_to_clusters", "read_pcd"]
 
 
 def _to_dev(eng: Engine, a, dtype=None):
@@ -318,6 +318,9 @@ def extract_cluster_data(labels, indices, vx, vy, engine=None):
     s = eng.cluster_summary(vxd, vyd, nv, lab, idx, n_clusters)
     eng.synchronize()
     s = s[0].cpu().numpy()
+    if np.any(s[:, 0] == 1):
+        # np.cov of one point is NaN and the reference's np.linalg.eigvals raises on it (main.py:424)
+        raise np.linalg.LinAlgError("Array must not contain infs or NaNs")
     eig = _eigvals_2x2(s[:, 5], s[:, 6], s[:, 7])
     out = {}
     for lab_id in range(n_clusters):
@@ -328,6 +331,23 @@ def extract_cluster_data(labels, indices, vx, vy, engine=None):
                        "measurement": [centroid[0], centroid[1], s[lab_id, 3], s[lab_id, 4]],
                        "eigenvalues": eig[lab_id]}
     return out
+
+
+def clusters_from_summary(summary, n_clusters: int, max_clusters: int | None = None) -> dict:
+    """{label: {'centroid', 'measurement', 'eigenvalues'}} (extract_cluster_data's result, main.py:402-434) from
+    the device's per-cluster rows [count, mean row, mean col, mean vx, mean vy, cov rr, rc, cc].
+    Two behaviours of the reference are kept: a cluster of ONE cell has a NaN covariance, on which
+    np.linalg.eigvals raises LinAlgError — the reference's per-pair try/except then skips the pair
+    (main.py:424, 635-637); and clusters are never dropped silently: more clusters than summary rows raise."""
+    if max_clusters is not None and n_clusters > max_clusters:
+        raise RuntimeError(f"{n_clusters} clusters but only {max_clusters} summary rows: raise max_clusters")
+    s = np.asarray(summary)[:n_clusters]
+    if len(s) and np.any(s[:, 0] == 1):
+        raise np.linalg.LinAlgError("Array must not contain infs or NaNs")
+    eig = _eigvals_2x2(s[:, 5], s[:, 6], s[:, 7]) if len(s) else np.zeros((0, 2))
+    return {i: {"centroid": np.array([s[i, 1], s[i, 2]]),
+                "measurement": [s[i, 1], s[i, 2], s[i, 3], s[i, 4]],
+                "eigenvalues": eig[i]} for i in range(len(s)) if s[i, 0] > 0}
 
 
 def flow_to_clusters(bev1, bev2, x_range, y_range, dt, alpha_cont, eps, min_samples, farneback=None, engine=None,
@@ -345,14 +365,10 @@ def flow_to_clusters(bev1, bev2, x_range, y_range, dt, alpha_cont, eps, min_samp
                             max_clusters=max_clusters, want_ang_f=return_grids)
     eng.synchronize()
     n = int(res.n_valid[0].item())
-    ncl = min(int(res.n_clusters[0].item()), max_clusters)
+    ncl = int(res.n_clusters[0].item())
     labels = res.labels[0, :n].cpu().numpy().astype(np.intp)
     indices = res.indices[0, :n].cpu().numpy().astype(np.int64)
-    s = res.summary[0, :ncl].cpu().numpy()
-    eig = _eigvals_2x2(s[:, 5], s[:, 6], s[:, 7]) if ncl else np.zeros((0, 2))
-    clusters = {i: {"centroid": np.array([s[i, 1], s[i, 2]]),
-                    "measurement": [s[i, 1], s[i, 2], s[i, 3], s[i, 4]],
-                    "eigenvalues": eig[i]} for i in range(ncl) if s[i, 0] > 0}
+    clusters = clusters_from_summary(res.summary[0, :min(ncl, max_clusters)].cpu().numpy(), ncl, max_clusters)
     if return_grids:
         # f64 like the reference's arrays (f32 * int64 mask); magnitude and curl computed on the device
         vxf, vyf = res.vx_f[0].to(torch.float64), res.vy_f[0].to(torch.float64)

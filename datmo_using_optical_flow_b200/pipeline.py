@@ -99,3 +99,141 @@ def process_clouds(clouds, config=None, engine=None, seed=0, ground_masks=None, 
         pairs.append(rec)
         prev = bev
     return dict(tracks=tm, pairs=pairs, bevs=bevs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# several sequences at once (BASELINE configs[4]: 8 concurrent 128-beam sequences at 20 Hz)
+# ---------------------------------------------------------------------------------------------------
+class SequenceRunner:
+    """The reference's driver loop (main.py:541-641) for SEVERAL sequences advancing in lock step on one
+    GPU.  Sequences are independent (the EKF state belongs to one sequence), so on every tick the k-th
+    sweep of each sequence is preprocessed to a device-resident BEV and the pairs (previous BEV, this BEV)
+    of ALL sequences go through flow -> velocity -> mask -> DBSCAN -> cluster summaries as ONE batched call;
+    only the per-cluster summaries (a few KB) come back to the host, where each sequence's tracker
+    (tracker.TrackManager, the reference's EKF semantics) consumes them.  One process per GPU owns a
+    shard of the sequences (sharding.shard_sequences); `sharding.gather_sequence_tracks` collects the
+    tracks of all shards once per tick.
+
+    sequence_ids: the job-wide ids of the sequences this runner owns (they seed the expansion noise, so a
+    sequence gives the same result however the job is sharded).  tick(clouds) takes one float32 (N,4)
+    sweep (numpy, or a CUDA tensor) per owned sequence — None for a dropped frame — and returns one record
+    per sequence."""
+
+    def __init__(self, sequence_ids, config=None, engine=None, seed: int = 0, max_clusters: int = 512,
+                 cap: int | None = None, keep_cells: bool = False, ground_masks=None):
+        import torch
+        self.torch = torch
+        self.cfg = dict(DEFAULT_CONFIG)
+        self.cfg.update(config or {})
+        self.eng = engine or default_engine()
+        self.ids = [int(s) for s in sequence_ids]
+        self.n = len(self.ids)
+        self.seed = int(seed)
+        self.max_clusters = int(max_clusters)
+        self.keep_cells = bool(keep_cells)
+        self.ground_masks = ground_masks     # optional {sequence id: [per-frame uint8 masks]} instead of RANSAC
+        self.trackers = [TrackManager() for _ in range(self.n)]
+        self.prev = [None] * self.n          # device BEV of the previous tick, per sequence
+        self.frame = 0
+        eng, cfg = self.eng, self.cfg
+        self.nx = eng.bev_bins(cfg["x_range"][0], cfg["x_range"][1], cfg["grid_resolution"][0])
+        self.ny = eng.bev_bins(cfg["y_range"][0], cfg["y_range"][1], cfg["grid_resolution"][1])
+        self.cap = self.nx * self.ny if cap is None else int(cap)
+        # main.py:147-150: pixel size = range / shape (the x range over axis 1, as the reference does)
+        self.px = (cfg["x_range"][1] - cfg["x_range"][0]) / self.ny
+        self.py = (cfg["y_range"][1] - cfg["y_range"][0]) / self.nx
+        self.last_ms = {}
+
+    def _bev(self, j: int, cloud):
+        torch, eng, cfg = self.torch, self.eng, self.cfg
+        if cloud is None:
+            return None
+        try:
+            pts = cloud if isinstance(cloud, torch.Tensor) else torch.from_numpy(cloud)
+            pts = pts.to(eng.tdev, dtype=torch.float32, non_blocking=True)
+            if pts.shape[1] == 3:
+                pts = torch.cat([pts, torch.zeros_like(pts[:, :1])], dim=1)
+            gm = None
+            if self.ground_masks is not None:
+                gm = torch.as_tensor(self.ground_masks[self.ids[j]][self.frame]).to(eng.tdev)
+            # the same seed process_clouds(seed=seed + 1000 * id) gives frame `self.frame` of this sequence
+            return eng.preprocess(pts, cfg["grid_resolution"], cfg["x_range"], cfg["y_range"], cfg["z_max"],
+                                  cfg["roi_bounds"], seed=self.seed + 1000 * self.ids[j] + self.frame, ground_mask=gm)
+        except Exception:       # the reference prints and moves on (main.py:635-637)
+            return None
+
+    def tick(self, clouds):
+        import time
+        import numpy as np
+        torch, eng, cfg = self.torch, self.eng, self.cfg
+        if len(clouds) != self.n:
+            raise ValueError(f"expected {self.n} sweeps, one per sequence")
+        t0 = time.perf_counter()
+        bevs = [self._bev(j, c) for j, c in enumerate(clouds)]
+        eng.synchronize()
+        t1 = time.perf_counter()
+        live = [j for j in range(self.n) if self.prev[j] is not None and bevs[j] is not None]
+        recs = [dict(sequence=self.ids[j], frame=self.frame, skipped=True) for j in range(self.n)]
+        t2 = t3 = t1
+        if live:
+            with eng.on_stream():
+                prev = torch.stack([self.prev[j] for j in live])
+                cur = torch.stack([bevs[j] for j in live])
+            res = eng.flow_pipeline(prev, cur, self.px, self.py, cfg["masks"]["alpha_cont"][0], cfg["dbscan_params"]["eps"],
+                                    cfg["dbscan_params"]["min_samples"], cap=self.cap, max_clusters=self.max_clusters,
+                                    keep_flow=False)
+            eng.synchronize()
+            ncl = res.n_clusters.cpu().numpy()
+            nval = res.n_valid.cpu().numpy()
+            kmax = int(min(ncl.max(), self.max_clusters))
+            summ = res.summary[:, :kmax].cpu().numpy() if kmax else np.zeros((len(live), 0, 8))
+            t2 = time.perf_counter()
+            for k, j in enumerate(live):
+                rec = recs[j]
+                try:
+                    if nval[k] == 0:
+                        raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by DBSCAN.")
+                    clusters = ops.clusters_from_summary(summ[k], int(ncl[k]), self.max_clusters)
+                    tm = self.trackers[j]
+                    tm.associate_and_update(clusters, cfg["dt"])       # main.py:618
+                    saved = tm.as_array()                                # what the savers see (main.py:619-620)
+                    tm.step_lifetimes()                                  # main.py:621-634
+                    rec.update(skipped=False, n_valid=int(nval[k]), n_clusters=int(ncl[k]), clusters=clusters,
+                               saved_tracks=saved, tracks=tm.as_array())
+                    if self.keep_cells:
+                        n = int(min(nval[k], self.cap))
+                        rec.update(labels=res.labels[k, :n].cpu().numpy().astype(np.intp),
+                                   indices=res.indices[k, :n].cpu().numpy().astype(np.int64))
+                except Exception as exc:       # per-pair failures skip the pair (main.py:635-637)
+                    rec["error"] = f"{type(exc).__name__}: {exc}"
+            t3 = time.perf_counter()
+        for j in range(self.n):
+            self.prev[j] = bevs[j]
+        self.frame += 1
+        self.last_ms = dict(preprocess=1e3 * (t1 - t0), flow_to_summaries=1e3 * (t2 - t1), tracker=1e3 * (t3 - t2),
+                            total=1e3 * (t3 - t0), pairs=len(live))
+        return recs
+
+
+def process_sequences(sequences, config=None, engine=None, seed=0, max_clusters=512, gather=True, max_tracks=64,
+                      ground_masks=None):
+    """sequences: list (over ALL sequences of the job) of equally long lists of float32 (N,4) sweeps.
+    Under torch.distributed each rank takes its shard (sharding.shard_sequences), runs its sequences in
+    lock step on its GPU and, once per tick, all-gathers the track tables (NCCL; the only collective).
+    Returns dict(local=[sequence ids], ticks=[per tick: one record per local sequence],
+    gathered=[per tick: {sequence id: (n,6) track table}], identical on every rank)."""
+    import torch.distributed as dist
+    from . import sharding
+    on = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    local = sharding.shard_sequences(len(sequences), rank, world)
+    runner = SequenceRunner(local, config, engine, seed=seed, max_clusters=max_clusters, ground_masks=ground_masks)
+    n_ticks = len(sequences[0]) if sequences else 0
+    ticks, gathered = [], []
+    for k in range(n_ticks):
+        recs = runner.tick([sequences[s][k] for s in local])
+        ticks.append(recs)
+        if gather:
+            tables = {s: runner.trackers[j].as_array() for j, s in enumerate(local)}
+            gathered.append(sharding.gather_sequence_tracks(tables, len(sequences), max_tracks))
+    return dict(local=local, ticks=ticks, gathered=gathered, runner=runner)

@@ -56,6 +56,41 @@ def gather_tracks(local: np.ndarray | torch.Tensor, max_tracks: int, device=None
     return res
 
 
+def gather_sequence_tracks(local: dict, n_sequences: int, max_tracks: int, device=None) -> dict:
+    """One all-gather per tick for every sequence of the job.  local: {sequence id: (n, 6) track table} of
+    the sequences this rank owns (a contiguous shard, sharding.shard_sequences).  Every rank contributes a
+    fixed block of ceil(n_sequences / world) slots x (2 + max_tracks * 6) float64 (sequence id, row count,
+    rows; NaN padded) and receives {sequence id: table} for all sequences."""
+    world = dist.get_world_size() if _is_dist() else 1
+    slots = -(-n_sequences // world) if n_sequences else 0
+    width = 2 + max_tracks * 6
+    buf = torch.full((max(slots, 1), width), float("nan"), dtype=torch.float64)
+    buf[:, 0] = -1
+    for k, (sid, table) in enumerate(sorted(local.items())):
+        t = torch.as_tensor(np.asarray(table, dtype=np.float64).reshape(-1, 6))
+        n = min(len(t), max_tracks)
+        buf[k, 0], buf[k, 1] = sid, n
+        buf[k, 2:2 + n * 6] = t[:n].reshape(-1)
+    if not _is_dist():
+        blocks = [buf]
+    else:
+        dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                 if dist.get_backend() == "nccl" else torch.device("cpu"))
+        send = buf.to(dev)
+        out = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(out, send)
+        blocks = [o.cpu() for o in out]
+    res = {}
+    for blk in blocks:
+        for row in blk:
+            sid = int(row[0].item())
+            if sid < 0:
+                continue
+            n = int(row[1].item())
+            res[sid] = row[2:2 + n * 6].reshape(n, 6).numpy().copy()
+    return res
+
+
 def reduce_metrics(values: dict[str, float], op: str = "sum", device=None) -> dict[str, float]:
     """All-reduce a small dict of scalars (timing, parity counters)."""
     keys = sorted(values)

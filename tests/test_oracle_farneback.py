@@ -81,6 +81,17 @@ def test_cv2_own_sensitivity_documents_the_floor():
     assert d.max() > 1e-5           # ulp-level input noise is amplified well beyond ulp level
 
 
+def test_oracle_within_north_star_tolerance_where_cv2_is_stable():
+    """The tolerance statement of the GPU tests, applied to the numpy restatement: max 1e-3 / mean 1e-5 px on
+    the pixels where cv2 is stable against a 1-ulp input perturbation; elsewhere cv2 itself moves by more."""
+    from oracle import flow_stability
+    a, b = synth.bev_pair(3, 800, 800)
+    r = flow_stability.compare(fb.calc_optical_flow_farneback(a, b, **REF), a, b, REF)
+    assert r["stable_fraction"] >= 0.9 and r["max_stable"] <= 1e-3 and r["mean_stable"] <= 1e-5, r
+    assert r["max_all"] > 1e-3 and r["ref_self_max"] > 1e-3       # this frame does have unstable pixels
+    assert r["max_unstable"] <= 20 * r["ref_self_max"], r
+
+
 def test_identical_and_zero_frames():
     z = np.zeros((64, 80), np.uint8)
     assert not fb.calc_optical_flow_farneback(z, z, **REF).any()      # all-zero frames -> exactly zero
