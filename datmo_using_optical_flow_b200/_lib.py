@@ -89,6 +89,8 @@ SIGNATURES = {
     "datmo_fb_flow_iter_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "datmo_fb_upsample_flow_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _d, _vp]),
     "datmo_velocity_mask_dev": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d] + [_vp] * 9),
+    "datmo_filtered_grids_f64_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "datmo_narrow_f64_dev": (_i, [_vp, _vp, _i64, _vp, C.POINTER(_i)]),
     "datmo_propagation_mask_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _vp]),
     "datmo_dbscan_grid_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _i, _vp, _vp, _vp, _vp]),
     "datmo_pack_indices_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp]),

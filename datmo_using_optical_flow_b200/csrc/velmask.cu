@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(256) k_velmask(const float2* __restrict__ flow
             const float div = __fadd_rn(dvx_dx, dvy_dy);
             const float curl = __fsub_rn(dvy_dx, dvx_dy);
             const int m = (fabsf(div) <= alpha) && (fabsf(curl) <= alpha);
-            const float vxf = m ? vx : 0.f, vyf = m ? vy : 0.f;
+            // v * mask as numpy computes it (main.py:600-601): a masked negative velocity is -0.0, a NaN stays NaN
+            const float mf = m ? 1.f : 0.f;
+            const float vxf = __fmul_rn(vx, mf), vyf = __fmul_rn(vy, mf);
             // sqrt is monotone and correctly rounded, so "sqrt(s) > thresh" is "s > s_crit" with s_crit the
             // largest double whose root is still <= thresh (found on the host): no DSQRT per cell.  The
             // f32 sum of squares (relative error < 2e-7) settles every cell that is not within 1e-6 of
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(256) k_velmask4(const float2* __restrict__ flo
             const float div = __fadd_rn(dvx_dx, dvy_dy);
             cu[j] = __fsub_rn(dvy_dx, dvx_dy);
             const int m = (fabsf(div) <= alpha) && (fabsf(cu[j]) <= alpha);
-            vxf[j] = m ? vx[j] : 0.f, vyf[j] = m ? vy[j] : 0.f;
+            const float mf = m ? 1.f : 0.f;   // v * mask like numpy: -0.0 for a masked negative velocity, NaN stays NaN
+            vxf[j] = __fmul_rn(vx[j], mf), vyf[j] = __fmul_rn(vy[j], mf);
             const float s32 = vxf[j] * vxf[j] + vyf[j] * vyf[j];   // see k_velmask for the threshold logic
             int is_valid;
             if (s32 > s_hi)
@@ -191,6 +194,54 @@ __global__ void __launch_bounds__(256) k_curl_filtered(const float* __restrict__
     else
         dvx_dy = (static_cast<double>(vx[o + W]) - vx[o - W]) / 2.0;
     ang_f[base + o] = static_cast<float>(dvy_dx - dvx_dy);
+}
+
+// The filtered field as the reference holds it (main.py:600-606): v * mask is float64 there (f32 * int64),
+// so are its magnitude and its curl (np.gradient of f64 arrays) — what the per-cell CSV and the .npy grids
+// hold.  One pass from the f32 filtered velocities; any output may be NULL.
+__global__ void __launch_bounds__(256) k_filtered_f64(const float* __restrict__ vxf, const float* __restrict__ vyf,
+                                                      int H, int W, double* __restrict__ vx64,
+                                                      double* __restrict__ vy64, double* __restrict__ mag64,
+                                                      double* __restrict__ ang64) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const size_t base = static_cast<size_t>(b) * H * W;
+    const size_t o = static_cast<size_t>(y) * W + x;
+    const float* vx = vxf + base;
+    const float* vy = vyf + base;
+    const double dx = vx[o], dy = vy[o];
+    if (vx64) vx64[base + o] = dx;
+    if (vy64) vy64[base + o] = dy;
+    if (mag64) mag64[base + o] = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    if (ang64) {
+        double dvy_dx, dvx_dy;
+        if (x == 0)
+            dvy_dx = static_cast<double>(vy[o + 1]) - vy[o];
+        else if (x == W - 1)
+            dvy_dx = static_cast<double>(vy[o]) - vy[o - 1];
+        else
+            dvy_dx = (static_cast<double>(vy[o + 1]) - vy[o - 1]) / 2.0;
+        if (y == 0)
+            dvx_dy = static_cast<double>(vx[o + W]) - vx[o];
+        else if (y == H - 1)
+            dvx_dy = static_cast<double>(vx[o]) - vx[o - W];
+        else
+            dvx_dy = (static_cast<double>(vx[o + W]) - vx[o - W]) / 2.0;
+        ang64[base + o] = dvy_dx - dvx_dy;
+    }
+}
+
+// f64 -> f32 with a check that nothing is lost (the reference's filtered velocities are f32 values held in
+// f64, main.py:600-601); *flag is raised when some value is not f32-representable (NaN counts as fine)
+__global__ void __launch_bounds__(256) k_narrow_checked(const double* __restrict__ src, size_t n,
+                                                        float* __restrict__ dst, int* __restrict__ flag) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = src[i];
+    const float f = static_cast<float>(v);
+    dst[i] = f;
+    if (static_cast<double>(f) != v && v == v) *flag = 1;
 }
 
 // ---- propagation masks (main.py:166-221) ---------------------------------------------------------
@@ -343,5 +394,35 @@ extern "C" int datmo_velocity_mask_dev(datmo_handle_t h, const float* flow, int 
         k_curl_filtered<<<g, 256, 0, h->stream>>>(vx_f, vy_f, H, W, ang_f);
         DATMO_POST_LAUNCH(h);
     }
+    return DATMO_OK;
+}
+
+extern "C" int datmo_filtered_grids_f64_dev(datmo_handle_t h, const float* vx_f, const float* vy_f, int H, int W,
+                                            int batch, double* vx64, double* vy64, double* mag64, double* ang64) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, vx_f && vy_f && H >= 2 && W >= 2 && batch >= 1, "need vx_f, vy_f, H, W >= 2 and batch >= 1");
+    DATMO_REQUIRE(h, H <= 65535 && batch <= 65535, "H and batch must fit a CUDA grid dimension");
+    dim3 g(ceil_div(W, 256), H, batch);
+    {
+        LaunchScope ls(h, DATMO_TAG_VELMASK);
+        k_filtered_f64<<<g, 256, 0, h->stream>>>(vx_f, vy_f, H, W, vx64, vy64, mag64, ang64);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+extern "C" int datmo_narrow_f64_dev(datmo_handle_t h, const double* src, int64_t n, float* dst, int* lossy) {
+    DATMO_ENTER(h);
+    DATMO_REQUIRE(h, src && dst && lossy && n >= 1, "bad arguments");
+    DATMO_TRY(datmo_ws_reserve(h, 256));
+    int* d_flag = reinterpret_cast<int*>(h->ws);
+    DATMO_CHECK_CUDA(h, cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
+    {
+        LaunchScope ls(h, DATMO_TAG_VELMASK);
+        k_narrow_checked<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, h->stream>>>(src, static_cast<size_t>(n), dst, d_flag);
+    }
+    DATMO_POST_LAUNCH(h);
+    DATMO_CHECK_CUDA(h, cudaMemcpyAsync(lossy, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    DATMO_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
     return DATMO_OK;
 }

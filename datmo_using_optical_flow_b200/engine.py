@@ -257,6 +257,30 @@ class Engine:
                 _ptr(out["vy_f"]), _ptr(out["ang_f"]), _ptr(out["valid"]), _ptr(out["n_valid"])))
         return {k: v for k, v in out.items() if v is not None}
 
+    def filtered_grids_f64(self, vx_f: torch.Tensor, vy_f: torch.Tensor, want=("vx", "vy", "mag", "ang")) -> dict:
+        """float64 view of the filtered field, its magnitude and curl (main.py:600-606), one launch."""
+        with self.on_stream():
+            squeeze = vx_f.dim() == 2
+            if squeeze:
+                vx_f, vy_f = vx_f.unsqueeze(0), vy_f.unsqueeze(0)
+            vx_f, vy_f = vx_f.contiguous(), vy_f.contiguous()
+            B, H, W = vx_f.shape
+            out = {k: (self.empty((B, H, W), torch.float64) if k in want else None) for k in ("vx", "vy", "mag", "ang")}
+            self._check(self.lib.datmo_filtered_grids_f64_dev(self.h, _ptr(vx_f), _ptr(vy_f), H, W, B, _ptr(out["vx"]),
+                                                              _ptr(out["vy"]), _ptr(out["mag"]), _ptr(out["ang"])))
+        return {k: (v[0] if squeeze else v) for k, v in out.items() if v is not None}
+
+    def narrow_f64(self, t: torch.Tensor) -> torch.Tensor:
+        """float64 -> float32 on the device; raises when a value is not float32-representable."""
+        with self.on_stream():
+            t = t.contiguous()
+            out = self.empty(t.shape, torch.float32)
+            lossy = C.c_int(0)
+            self._check(self.lib.datmo_narrow_f64_dev(self.h, _ptr(t), t.numel(), _ptr(out), C.byref(lossy)))
+        if lossy.value:
+            raise ValueError("velocities must be float32-representable (they are f32 flow * mask in the reference)")
+        return out
+
     def propagation_mask(self, vx: torch.Tensor, vy: torch.Tensor, dt: float, grid_resolution, alpha_p: float,
                          ax: torch.Tensor | None = None, ay: torch.Tensor | None = None) -> torch.Tensor:
         """[B,H,W] (or [H,W]) f32 / f64 velocities (and accelerations) -> uint8 mask, see datmo_propagation_mask_dev."""

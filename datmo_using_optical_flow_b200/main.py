@@ -247,11 +247,11 @@ def moving_cell_filter(vx, vy, alpha_cont, thresh=0.1, engine=None):
     eng = engine or default_engine()
     as_np = _is_np(vx, vy)
     flow = _velocity_as_flow(eng, vx, vy)
-    vm = eng.velocity_mask(flow, 1.0, 1.0, alpha_cont, thresh, want=("vx_f", "vy_f", "ang_f", "valid"))
+    vm = eng.velocity_mask(flow, 1.0, 1.0, alpha_cont, thresh, want=("vx_f", "vy_f", "valid"))
     sq = (lambda t: t[0]) if flow.dim() == 3 else (lambda t: t)
-    vxf, vyf = sq(vm["vx_f"]).to(torch.float64), sq(vm["vy_f"]).to(torch.float64)
-    mag = torch.sqrt(vxf * vxf + vyf * vyf)
-    ang, valid = sq(vm["ang_f"]).to(torch.float64), sq(vm["valid"]).to(torch.bool)
+    g = eng.filtered_grids_f64(vm["vx_f"], vm["vy_f"])       # f64 like the reference's arrays, one launch
+    vxf, vyf, mag, ang = sq(g["vx"]), sq(g["vy"]), sq(g["mag"]), sq(g["ang"])
+    valid = sq(vm["valid"]).view(torch.bool)
     if as_np:
         eng.synchronize()
         return tuple(t.cpu().numpy() for t in (vxf, vyf, mag, ang, valid))
@@ -269,13 +269,12 @@ def dbscan_clustering(vx_filtered, vy_filtered, valid_mask, eps=1.0, min_samples
     as_np = _is_np(vx_filtered, vy_filtered, valid_mask)
     vx = _to_dev(eng, vx_filtered)
     vy = _to_dev(eng, vy_filtered)
-    if vx.dtype == torch.float64:
-        # the reference's filtered velocities are float32 values held in float64 (main.py:600-601)
-        if not (torch.equal(vx.to(torch.float32).to(torch.float64), vx)
-                and torch.equal(vy.to(torch.float32).to(torch.float64), vy)):
-            raise ValueError("velocities must be float32-representable (they are f32 flow * mask in the reference)")
-    vx, vy = vx.to(torch.float32), vy.to(torch.float32)
-    valid = _to_dev(eng, valid_mask).to(torch.uint8)
+    # the reference's filtered velocities are float32 values held in float64 (main.py:600-601): narrowed on the
+    # device with a check, one launch each
+    vx = eng.narrow_f64(vx) if vx.dtype == torch.float64 else vx.to(torch.float32)
+    vy = eng.narrow_f64(vy) if vy.dtype == torch.float64 else vy.to(torch.float32)
+    valid = _to_dev(eng, valid_mask)
+    valid = valid.view(torch.uint8) if valid.dtype == torch.bool else valid.to(torch.uint8)
     n_valid, labels, indices, _ = eng.dbscan_grid(vx, vy, valid, eps, min_samples)
     eng.synchronize()
     n = int(n_valid[0].item())
@@ -362,7 +361,7 @@ def flow_to_clusters(bev1, bev2, x_range, y_range, dt, alpha_cont, eps, min_samp
     px = (x_range[1] - x_range[0]) / W
     py = (y_range[1] - y_range[0]) / H
     res = eng.flow_pipeline(a, b, px, py, alpha_cont, eps, min_samples, farneback_params(**(farneback or {})),
-                            max_clusters=max_clusters, want_ang_f=return_grids)
+                            max_clusters=max_clusters)
     eng.synchronize()
     n = int(res.n_valid[0].item())
     ncl = int(res.n_clusters[0].item())
@@ -370,10 +369,10 @@ def flow_to_clusters(bev1, bev2, x_range, y_range, dt, alpha_cont, eps, min_samp
     indices = res.indices[0, :n].cpu().numpy().astype(np.int64)
     clusters = clusters_from_summary(res.summary[0, :min(ncl, max_clusters)].cpu().numpy(), ncl, max_clusters)
     if return_grids:
-        # f64 like the reference's arrays (f32 * int64 mask); magnitude and curl computed on the device
-        vxf, vyf = res.vx_f[0].to(torch.float64), res.vy_f[0].to(torch.float64)
-        grids = dict(vx_filtered=vxf.cpu().numpy(), vy_filtered=vyf.cpu().numpy(),
-                     velocity_magnitude=torch.sqrt(vxf * vxf + vyf * vyf).cpu().numpy(),
-                     angular_velocity=res.ang_f[0].to(torch.float64).cpu().numpy())
+        # f64 like the reference's arrays (f32 * int64 mask), magnitude and f64 curl: one device launch
+        g = eng.filtered_grids_f64(res.vx_f[0], res.vy_f[0])
+        eng.synchronize()
+        grids = dict(vx_filtered=g["vx"].cpu().numpy(), vy_filtered=g["vy"].cpu().numpy(),
+                     velocity_magnitude=g["mag"].cpu().numpy(), angular_velocity=g["ang"].cpu().numpy())
         return labels, indices, clusters, grids
     return labels, indices, clusters

@@ -142,6 +142,16 @@ int datmo_velocity_mask_dev(datmo_handle_t h, const float* flow, int H, int W, i
                             float* ang, uint8_t* mask, float* vx_f, float* vy_f, float* ang_f,
                             uint8_t* valid, int32_t* n_valid);
 
+/* The filtered field in the dtype the reference holds it in (main.py:600-606: f32 * int64 mask -> float64,
+ * its magnitude and the np.gradient curl of the f64 arrays) — what save_velocity_grid and the per-cell CSV
+ * receive.  vx_f, vy_f: float [batch][H][W] from datmo_velocity_mask_dev; outputs double [batch][H][W],
+ * any may be NULL. */
+int datmo_filtered_grids_f64_dev(datmo_handle_t h, const float* vx_f, const float* vy_f, int H, int W,
+                                 int batch, double* vx64, double* vy64, double* mag64, double* ang64);
+/* double -> float for the velocities dbscan_clustering receives (main.py:231: f32 values held in f64);
+ * *lossy (host) is set when a value is not float32-representable.  Synchronises. */
+int datmo_narrow_f64_dev(datmo_handle_t h, const double* src, int64_t n, float* dst, int* lossy);
+
 /* ---- propagation masks ---------------------------------------------------------
  * Replaces propagation_mask (main.py:166-182) and propagation_mask_with_acceleration
  * (main.py:184-221; pass ax = ay = NULL for the former).  The reference defines both

@@ -37,10 +37,14 @@ def self_deviation(prev, nxt, cv_params: dict, trials: int = TRIALS, amp: float 
 
 
 def compare(flow, prev, nxt, cv_params: dict, stable_tol: float = STABLE_TOL) -> dict:
-    """Deviation of `flow` from cv2 on the frame pair, split by cv2's own stability."""
+    """Deviation of `flow` from cv2 on the frame pair, split by cv2's own stability.  A pixel counts as
+    stable when cv2 moved by <= stable_tol in every trial at every pixel of its own winsize x winsize
+    window (the flow of a pixel is solved from sums over that window, so an unstable neighbour reaches it)."""
+    from scipy.ndimage import maximum_filter
     ref, s = self_deviation(prev, nxt, cv_params)
     d = np.abs(np.asarray(flow) - ref).max(axis=2)
-    stable = s <= stable_tol
+    win = 2 * (int(cv_params.get("winsize", 15)) // 2) + 1
+    stable = maximum_filter(s, size=win, mode="nearest") <= stable_tol
     out = dict(stable_fraction=float(stable.mean()), max_stable=float(d[stable].max()) if stable.any() else 0.0,
                mean_stable=float(d[stable].mean()) if stable.any() else 0.0, max_all=float(d.max()),
                mean_all=float(d.mean()), p999_all=float(np.quantile(d, 0.999)),

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES out of sync with the header"
-    assert lib.datmo_abi_version() == 1
+    assert lib.datmo_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_host_side_helpers_without_gpu():

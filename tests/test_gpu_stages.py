@@ -389,6 +389,33 @@ def test_sequence_pipeline_tracks_the_mover(engine, tmp_path):
     assert (tmp_path / "filtered_velocities.csv").read_text().startswith("Frame Index,Point Index,Filtered X Velocity")
 
 
+def test_process_sequences_batched_equals_single_sequence_runs(engine):
+    """BASELINE configs[4] in miniature: three sequences advanced in lock step — one batched flow -> clusters call
+    per tick — must give, for every sequence, exactly the tracks of driving that sequence on its own
+    (process_clouds): sharding / batching must not change results."""
+    from datmo_using_optical_flow_b200.pipeline import process_clouds, process_sequences
+    cfg = dict(grid_resolution=[0.25, 0.25], x_range=[-50.0, 50.0], y_range=[-50.0, 50.0], z_max=2.0,
+               roi_bounds=[-50, 50, -50, 50, -3, 1], dt=1.0)
+    n_seq, n_frames = 3, 5
+    seqs = [[synth.lidar_sweep(10 + s, f, 32, 30_000, 1 + s, dt=0.1) for f in range(n_frames)] for s in range(n_seq)]
+    seqs[1][2] = None            # a dropped frame: pairs 1 and 2 of that sequence are skipped (main.py:572-574)
+    out = process_sequences(seqs, cfg, engine=engine, seed=4)
+    assert out["local"] == [0, 1, 2] and len(out["ticks"]) == n_frames and len(out["gathered"]) == n_frames
+    n_done = 0
+    for s in range(n_seq):
+        single = process_clouds([c for c in seqs[s]], cfg, engine=engine, seed=4 + 1000 * s)
+        for k in range(1, n_frames):
+            rec, want = out["ticks"][k][s], single["pairs"][k - 1]
+            assert rec["skipped"] == want["skipped"], (s, k, rec.get("error"))
+            if not rec["skipped"]:
+                n_done += 1
+                assert np.array_equal(rec["tracks"], want["tracks"]) and np.array_equal(rec["saved_tracks"], want["saved_tracks"])
+                assert sorted(rec["clusters"]) == sorted(want["clusters"])
+        assert np.array_equal(out["gathered"][-1][s], single["tracks"].as_array())
+    assert n_done >= 6
+    assert out["runner"].last_ms["pairs"] >= 2
+
+
 @pytest.mark.parametrize("want_cells", [True, False])
 def test_host_flow_pipeline_matches_device_chain(engine, want_cells):
     """The host-buffer entry (bench.py's e2e leg, a thin caller of the C-ABI chain): pinned uint8 in, compact

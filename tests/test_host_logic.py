@@ -115,6 +115,74 @@ def test_gloo_world2_gather_and_reduce(tmp_path):
         assert d["g1"][2, 0] == 12.0
 
 
+def _gloo_sequences_worker(rank, world, port, out_dir):
+    """The N > 1 host logic of pipeline.process_sequences without a GPU: every rank drives the trackers of its
+    shard of 5 sequences with canned cluster dictionaries and all-gathers the track tables once per tick."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_seq, n_ticks = 5, 6
+        local = sharding.shard_sequences(n_seq, rank, world)
+        tms = {s: TrackManager() for s in local}
+        out = {}
+        for k in range(n_ticks):
+            for s in local:
+                tms[s].update(_canned_clusters(s, k), 1.0)
+            got = sharding.gather_sequence_tracks({s: tms[s].as_array() for s in local}, n_seq, max_tracks=8)
+            assert sorted(got) == list(range(n_seq))
+            for s, t in got.items():
+                out[f"t{k}_s{s}"] = t
+        np.savez(os.path.join(out_dir, f"seq_r{rank}.npz"), **out)
+    finally:
+        dist.destroy_process_group()
+
+
+def _canned_clusters(seq, tick):
+    rng = np.random.default_rng(100 * seq + 7)
+    base = rng.uniform(20, 80, (3, 2))
+    cl = {}
+    for j in range(1 + (seq + tick) % 3):
+        c = base[j] + 0.01 * tick
+        cl[j] = dict(centroid=c, measurement=[c[0], c[1], 0.0, 0.0], eigenvalues=np.array([0.02, 0.03]))
+    return cl
+
+
+def test_gloo_world2_sequence_shards_gather_every_tick(tmp_path):
+    world = 2
+    mp.spawn(_gloo_sequences_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "seq_r0.npz"), np.load(tmp_path / "seq_r1.npz")
+    assert sorted(r0.files) == sorted(r1.files) and len(r0.files) == 5 * 6
+    # the single-process run of every sequence
+    for s in range(5):
+        tm = TrackManager()
+        for k in range(6):
+            tm.update(_canned_clusters(s, k), 1.0)
+            want = tm.as_array()
+            for r in (r0, r1):       # every rank holds every sequence's table, equal to the unsharded run
+                assert np.array_equal(r[f"t{k}_s{s}"], want)
+
+
+def test_gather_sequence_tracks_single_process():
+    tabs = {0: np.arange(12, dtype=np.float64).reshape(2, 6), 1: np.zeros((0, 6))}
+    got = sharding.gather_sequence_tracks(tabs, 2, max_tracks=4)
+    assert np.array_equal(got[0], tabs[0]) and got[1].shape == (0, 6)
+
+
+def test_clusters_from_summary_reference_behaviours():
+    from datmo_using_optical_flow_b200.main import clusters_from_summary
+    s = np.array([[5, 10.0, 20.0, 0.5, -0.25, 2.0, 0.5, 1.0], [3, 1.0, 2.0, 0.0, 0.0, 1.0, 0.0, 1.0]])
+    cl = clusters_from_summary(s, 2, 8)
+    assert list(cl) == [0, 1] and cl[0]["measurement"] == [10.0, 20.0, 0.5, -0.25]
+    lam = np.linalg.eigvals(np.array([[2.0, 0.5], [0.5, 1.0]]))
+    assert np.allclose(np.sort(cl[0]["eigenvalues"]), np.sort(lam))
+    one = np.array([[1, 3.0, 4.0, 0.1, 0.1, np.nan, np.nan, np.nan]])
+    with pytest.raises(np.linalg.LinAlgError):      # the reference's eigvals raises on the NaN covariance (main.py:424)
+        clusters_from_summary(one, 1, 8)
+    with pytest.raises(RuntimeError):               # more clusters than summary rows is an error, not a truncation
+        clusters_from_summary(s, 9, 8)
+
+
 def test_gather_tracks_single_process_and_truncation():
     t = np.arange(30, dtype=np.float64).reshape(5, 6)
     out = sharding.gather_tracks(t, max_tracks=3)

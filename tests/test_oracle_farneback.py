@@ -87,7 +87,7 @@ def test_oracle_within_north_star_tolerance_where_cv2_is_stable():
     from oracle import flow_stability
     a, b = synth.bev_pair(3, 800, 800)
     r = flow_stability.compare(fb.calc_optical_flow_farneback(a, b, **REF), a, b, REF)
-    assert r["stable_fraction"] >= 0.9 and r["max_stable"] <= 1e-3 and r["mean_stable"] <= 1e-5, r
+    assert r["stable_fraction"] >= 0.75 and r["max_stable"] <= 1e-3 and r["mean_stable"] <= 1e-5, r
     assert r["max_all"] > 1e-3 and r["ref_self_max"] > 1e-3       # this frame does have unstable pixels
     assert r["max_unstable"] <= 20 * r["ref_self_max"], r
 
