@@ -11,6 +11,7 @@
 // waits for the counters, sizes the read-back from them and issues one device-to-host copy per array
 // on a second copy stream.  With two slots the copies of batch i overlap the kernels of batch i + 1.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -43,7 +44,16 @@ struct datmo_chain {
         double* h_summary = nullptr;
         cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
         bool busy = false;
+        // the slot's launch train as a CUDA graph: captured on the second submission (the first one grows
+        // the workspace, opts kernels into large shared memory and uploads the per-layer tables) and replayed
+        // while the buffers it was captured against are still the handle's
+        cudaGraphExec_t graph = nullptr;
+        const char* graph_ws = nullptr;
+        const float* graph_tab = nullptr;
+        int64_t graph_launches = 0;
+        int runs = 0;
     };
+    bool use_graph = true;
     std::vector<Slot> slots;
     std::string err;
 };
@@ -143,6 +153,48 @@ int chain_fail(datmo_chain* c, int status, const char* what) {
 
 }  // namespace
 
+// everything one submission runs on the handle's stream, from the frames in the slot's device buffers to
+// the counters in its pinned mirror
+static int chain_enqueue(datmo_chain* c, datmo_chain::Slot& s) {
+    datmo_ctx* h = c->h;
+    const datmo_chain_config& g = c->cfg;
+    const int B = g.batch;
+    int st = datmo_farneback_dev(h, s.prev, s.next, g.dtype, g.H, g.W, B, &g.fb, c->flow);
+    if (st == DATMO_OK)
+        st = datmo_velocity_mask_dev(h, c->flow, g.H, g.W, B, g.px_x, g.px_y, g.alpha_cont, g.thresh, nullptr, nullptr,
+                                     nullptr, nullptr, c->vx_f, c->vy_f, nullptr, c->valid, nullptr);
+    if (st == DATMO_OK)
+        st = datmo_dbscan_grid_dev(h, c->vx_f, c->vy_f, c->valid, g.H, g.W, B, g.eps, g.min_samples, g.cap, c->n_valid,
+                                   c->labels, c->indices, c->n_clusters);
+    if (st == DATMO_OK && g.max_clusters > 0)
+        st = datmo_cluster_summary_dev(h, c->vx_f, c->vy_f, g.H, g.W, B, g.cap, c->n_valid, c->labels, c->indices,
+                                       g.max_clusters, c->summary);
+    if (st != DATMO_OK) {
+        c->err = h->err;
+        return st;
+    }
+    {
+        LaunchScope ls(h, DATMO_TAG_CLUSTER);
+        k_chain_plan<<<1, 256, 0, h->stream>>>(c->n_valid, c->n_clusters, B, g.cap, g.max_clusters, s.d_counts, s.d_offsets);
+    }
+    CHAIN_CUDA(c, cudaGetLastError());
+    if (g.want_cells) {
+        LaunchScope ls(h, DATMO_TAG_CLUSTER);
+        const dim3 grid(std::max(1, std::min(64, ceil_div(4 * h->sm_count, B))), B);
+        k_chain_gather<<<grid, 256, 0, h->stream>>>(c->labels, reinterpret_cast<const int2*>(c->indices), c->n_valid, g.cap,
+                                                   B, s.d_counts, s.d_offsets, s.d_labels, s.d_cells);
+    }
+    CHAIN_CUDA(c, cudaGetLastError());
+    if (g.max_clusters > 0) {
+        LaunchScope ls(h, DATMO_TAG_CLUSTER);
+        k_chain_gather_summary<<<dim3(4, B), 256, 0, h->stream>>>(c->summary, g.max_clusters, B, s.d_counts, s.d_summary);
+    }
+    CHAIN_CUDA(c, cudaGetLastError());
+    CHAIN_CUDA(c, cudaMemcpyAsync(s.h_counts, s.d_counts, (2 * B + 2) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CHAIN_CUDA(c, cudaMemcpyAsync(s.h_offsets, s.d_offsets, (B + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    return DATMO_OK;
+}
+
 extern "C" {
 
 void datmo_chain_default_config(datmo_chain_config* cfg) {
@@ -170,6 +222,7 @@ int datmo_chain_destroy(datmo_chain_t c) {
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+        if (s.graph) cudaGraphExecDestroy(s.graph);
     }
     if (c->dev) cudaFree(c->dev);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -251,6 +304,7 @@ int datmo_chain_create(datmo_handle_t h, const datmo_chain_config* cfg, datmo_ch
             cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming) != cudaSuccess)
             return bail("cudaEventCreate failed");
+    c->use_graph = getenv("DATMO_CHAIN_GRAPH") ? atoi(getenv("DATMO_CHAIN_GRAPH")) != 0 : true;
     *out = c;
     return DATMO_OK;
 }
@@ -271,39 +325,45 @@ int datmo_chain_submit(datmo_chain_t c, int slot, const void* prev_host, const v
     CHAIN_CUDA(c, cudaMemcpyAsync(s.next, next_host, c->in_bytes, cudaMemcpyHostToDevice, c->h2d));
     CHAIN_CUDA(c, cudaEventRecord(s.ev_h2d, c->h2d));
     CHAIN_CUDA(c, cudaStreamWaitEvent(h->stream, s.ev_h2d, 0));
-    int st = datmo_farneback_dev(h, s.prev, s.next, g.dtype, g.H, g.W, B, &g.fb, c->flow);
-    if (st == DATMO_OK)
-        st = datmo_velocity_mask_dev(h, c->flow, g.H, g.W, B, g.px_x, g.px_y, g.alpha_cont, g.thresh, nullptr, nullptr,
-                                     nullptr, nullptr, c->vx_f, c->vy_f, nullptr, c->valid, nullptr);
-    if (st == DATMO_OK)
-        st = datmo_dbscan_grid_dev(h, c->vx_f, c->vy_f, c->valid, g.H, g.W, B, g.eps, g.min_samples, g.cap, c->n_valid,
-                                   c->labels, c->indices, c->n_clusters);
-    if (st == DATMO_OK && g.max_clusters > 0)
-        st = datmo_cluster_summary_dev(h, c->vx_f, c->vy_f, g.H, g.W, B, g.cap, c->n_valid, c->labels, c->indices,
-                                       g.max_clusters, c->summary);
-    if (st != DATMO_OK) {
-        c->err = h->err;
-        return st;
+    // the kernels of one submission: replayed as a graph when one is at hand, else launched (and, from the
+    // second submission on, captured)
+    const bool graphs = c->use_graph && !h->prof;
+    if (graphs && s.graph && s.graph_ws == h->ws && s.graph_tab == h->fb_tab) {
+        CHAIN_CUDA(c, cudaGraphLaunch(s.graph, h->stream));
+        h->launches += s.graph_launches;
+    } else {
+        if (s.graph) {
+            cudaGraphExecDestroy(s.graph);
+            s.graph = nullptr;
+        }
+        const bool capture = graphs && s.runs >= 1;
+        const int64_t launches0 = h->launches;
+        if (capture) CHAIN_CUDA(c, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int st = chain_enqueue(c, s);
+        if (capture) {
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+            if (st == DATMO_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&s.graph, graph, 0) == cudaSuccess) {
+                s.graph_ws = h->ws;
+                s.graph_tab = h->fb_tab;
+                s.graph_launches = h->launches - launches0;
+                st = cudaGraphLaunch(s.graph, h->stream) == cudaSuccess ? DATMO_OK : DATMO_E_CUDA;
+            } else {
+                // capture refused (something in the train synchronised or allocated): plain launches from now on
+                cudaGetLastError();
+                s.graph = nullptr;
+                c->use_graph = false;
+                h->launches = launches0;
+                st = chain_enqueue(c, s);
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (st != DATMO_OK) {
+            if (c->err.empty()) c->err = h->err;
+            return st;
+        }
+        ++s.runs;
     }
-    {
-        LaunchScope ls(h, DATMO_TAG_CLUSTER);
-        k_chain_plan<<<1, 256, 0, h->stream>>>(c->n_valid, c->n_clusters, B, g.cap, g.max_clusters, s.d_counts, s.d_offsets);
-    }
-    CHAIN_CUDA(c, cudaGetLastError());
-    if (g.want_cells) {
-        LaunchScope ls(h, DATMO_TAG_CLUSTER);
-        const dim3 grid(std::max(1, std::min(64, ceil_div(4 * h->sm_count, B))), B);
-        k_chain_gather<<<grid, 256, 0, h->stream>>>(c->labels, reinterpret_cast<const int2*>(c->indices), c->n_valid, g.cap,
-                                                   B, s.d_counts, s.d_offsets, s.d_labels, s.d_cells);
-    }
-    CHAIN_CUDA(c, cudaGetLastError());
-    if (g.max_clusters > 0) {
-        LaunchScope ls(h, DATMO_TAG_CLUSTER);
-        k_chain_gather_summary<<<dim3(4, B), 256, 0, h->stream>>>(c->summary, g.max_clusters, B, s.d_counts, s.d_summary);
-    }
-    CHAIN_CUDA(c, cudaGetLastError());
-    CHAIN_CUDA(c, cudaMemcpyAsync(s.h_counts, s.d_counts, (2 * B + 2) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    CHAIN_CUDA(c, cudaMemcpyAsync(s.h_offsets, s.d_offsets, (B + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CHAIN_CUDA(c, cudaEventRecord(s.ev_done, h->stream));
     s.busy = true;
     return DATMO_OK;

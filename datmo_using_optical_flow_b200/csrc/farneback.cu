@@ -694,6 +694,242 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp(const SrcT* __restr
 }
 
 // ------------------------------------------------------------------------------------
+// The same, with the output staged through shared memory and written by the bulk-copy engine
+// (cp.async.bulk, SASS UBLKCP), prev and next frames in one launch.
+//
+// The kernel is bound by the L1 data stage (shared-memory wavefronts + one wavefront per 128-byte
+// line a global store instruction touches).  Two changes against k_pyr0_polyexp:
+//   * the horizontal pass gives a thread 8 adjacent outputs (15 16-byte shared loads per 8 pixels
+//     instead of 24); a quarter-warp is eight ROWS of one 8-pixel block, and the row strides of the
+//     r arrays and of the staging tile are odd numbers of 16-byte chunks, so the 16-byte loads and
+//     stores of a quarter-warp fall into eight different bank groups;
+//   * a thread's 8 x (float4 + float) results go to a staging tile in shared memory (it takes the
+//     place of the raw / blurred image, dead by then) and one lane per row hands the finished row —
+//     1 KiB of float4 coefficients, 256 bytes of the fifth — to the bulk-copy engine: the global
+//     stores no longer pass through the LSU, where a thread-contiguous 128-byte store costs a
+//     wavefront per lane.
+// ------------------------------------------------------------------------------------
+template <int N>
+struct P0T {
+    static constexpr int TY = P0Tile<N>::TY;
+    static constexpr int RW = P0_TX + 2 * N, RH = TY + 2 * N;
+    static constexpr int OX = (N + 1 + 3) & ~3;
+    static constexpr int NWD = (P0_TX + OX + N + 1 + 3) / 4;
+    static constexpr int SWS = NWD * 4 + 4, SHS = RH + 2;
+    static constexpr int RWP = 4 * ((((RW + 3) / 4)) | 1);   // odd number of 16-byte chunks per r row
+    static constexpr int QS = P0_TX + 1;                     // staging row stride, float4 (65 chunks)
+    static constexpr int SS = P0_TX + 4;                     // staging row stride of the fifth coefficient, floats
+    static constexpr int A_FLOATS_IN = SHS * SWS + RH * RW;  // raw + blurred image
+    static constexpr int A_FLOATS_OUT = TY * QS * 4 + TY * SS;
+    static constexpr int A_FLOATS = ((A_FLOATS_IN > A_FLOATS_OUT ? A_FLOATS_IN : A_FLOATS_OUT) + 3) & ~3;
+    static constexpr size_t SMEM = static_cast<size_t>(A_FLOATS + 3 * TY * RWP) * sizeof(float);
+    static_assert(TY % 8 == 0 && (TY / 8) * 2 <= P0_THREADS / 32, "horizontal pass: 8 rows x 4 blocks per warp");
+};
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(static_cast<unsigned>(__cvta_generic_to_shared(ssrc))), "r"(bytes)
+                 : "memory");
+}
+
+template <typename SrcT, int N>
+__global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp_t(const SrcT* __restrict__ src0,
+                                                               const SrcT* __restrict__ src1, int n0,
+                                                               float* __restrict__ R, int w, int h,
+                                                               int imgs_per_array, PolyCoef pc) {
+    using T = P0T<N>;
+    constexpr int P0_TY = T::TY, RW = T::RW, RH = T::RH, OX = T::OX, NWD = T::NWD, SWS = T::SWS, SHS = T::SHS,
+                  RWP = T::RWP;
+    extern __shared__ __align__(128) float smem0[];
+    float* sS = smem0;                        // [SHS][SWS] raw frame region
+    float* sI = smem0 + SHS * SWS;            // [RH][RW] blurred image
+    float* sr = smem0 + T::A_FLOATS;          // [3][P0_TY][RWP]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * P0_TX, y0 = blockIdx.y * P0_TY, b = blockIdx.z;
+    const int ox = x0 - OX, oy = y0 - N - 1;
+    const size_t plane = static_cast<size_t>(w) * h;
+    // images 0 .. n0-1 come from src0, the rest from src1 (prev and next frames in one launch)
+    const SrcT* sb = (b < n0 ? src0 + b * plane : src1 + (b - n0) * plane);
+    constexpr int TRIPS = (SHS * NWD + P0_THREADS - 1) / P0_THREADS;
+    if (ox >= 0 && ox + NWD * 4 <= w && oy >= 0 && oy + SHS <= h) {
+        float4 v[TRIPS];
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * P0_THREADS;
+            if (i < SHS * NWD) {
+                const int yy = i / NWD, wd = i - yy * NWD;
+                const SrcT* p = sb + static_cast<size_t>(oy + yy) * w + ox + wd * 4;
+                if (sizeof(SrcT) == 1) {
+                    const uchar4 u = *reinterpret_cast<const uchar4*>(p);
+                    v[t] = make_float4(u.x, u.y, u.z, u.w);
+                } else {
+                    v[t] = *reinterpret_cast<const float4*>(p);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * P0_THREADS;
+            if (i < SHS * NWD) {
+                const int yy = i / NWD, wd = i - yy * NWD;
+                *reinterpret_cast<float4*>(sS + yy * SWS + wd * 4) = v[t];
+            }
+        }
+    } else {
+        // border ring: rows reflect as a whole (still one 4-pixel load per word); only the words that
+        // straddle the left / right image edge reflect pixel by pixel
+        float4 v[TRIPS];
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * P0_THREADS;
+            if (i < SHS * NWD) {
+                const int yy = i / NWD, wd = i - yy * NWD;
+                const int gy = reflect101(oy + yy, h), gx0 = ox + wd * 4;
+                const SrcT* row = sb + static_cast<size_t>(gy) * w;
+                if (gx0 >= 0 && gx0 + 3 < w) {
+                    if (sizeof(SrcT) == 1) {
+                        const uchar4 u = *reinterpret_cast<const uchar4*>(row + gx0);
+                        v[t] = make_float4(u.x, u.y, u.z, u.w);
+                    } else {
+                        v[t] = *reinterpret_cast<const float4*>(row + gx0);
+                    }
+                } else {
+                    v[t] = make_float4(load_px(row + reflect101(gx0, w)), load_px(row + reflect101(gx0 + 1, w)),
+                                       load_px(row + reflect101(gx0 + 2, w)), load_px(row + reflect101(gx0 + 3, w)));
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            const int i = tid + t * P0_THREADS;
+            if (i < SHS * NWD) {
+                const int yy = i / NWD, wd = i - yy * NWD;
+                *reinterpret_cast<float4*>(sS + yy * SWS + wd * 4) = v[t];
+            }
+        }
+    }
+    __syncthreads();
+    // blurred image at replicate-clamped coordinates (what polyExp's border handling reads)
+    const bool no_clamp = x0 - N >= 0 && x0 - N + RW <= w && y0 - N >= 0 && y0 - N + RH <= h;
+    if (no_clamp) {
+        constexpr int CH = 4, RPC = (RH + CH - 1) / CH;  // row chunks per column, rows per chunk
+        for (int i = tid; i < CH * RW; i += P0_THREADS) {
+            const int ch = i / RW, xx = i - ch * RW;
+            const int r0 = ch * RPC;
+            const float* c = sS + (r0 + 1) * SWS + (xx + OX - N);   // raw pixel under blurred (r0, xx)
+            float tm = 0.25f * c[-SWS - 1] + 0.5f * c[-SWS] + 0.25f * c[-SWS + 1];
+            float t0 = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
+#pragma unroll
+            for (int k = 0; k < RPC; ++k) {
+                const int yy = r0 + k;
+                if (yy >= RH) break;
+                c += SWS;
+                const float tp = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
+                sI[yy * RW + xx] = 0.25f * tm + 0.5f * t0 + 0.25f * tp;
+                tm = t0;
+                t0 = tp;
+            }
+        }
+    } else {
+        for (int i = tid; i < RH * RW; i += P0_THREADS) {
+            const int yy = i / RW, xx = i - yy * RW;
+            const int gy = min(max(y0 - N + yy, 0), h - 1), gx = min(max(x0 - N + xx, 0), w - 1);
+            const float* c = sS + (gy - oy) * SWS + (gx - ox);
+            const float t0 = 0.25f * c[-SWS - 1] + 0.5f * c[-SWS] + 0.25f * c[-SWS + 1];
+            const float t1 = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
+            const float t2 = 0.25f * c[SWS - 1] + 0.5f * c[SWS] + 0.25f * c[SWS + 1];
+            sI[i] = 0.25f * t0 + 0.5f * t1 + 0.25f * t2;
+        }
+    }
+    __syncthreads();
+    // vertical pass: 4 output rows per item
+    for (int i = tid; i < (P0_TY / 4) * RW; i += P0_THREADS) {
+        const int g = i / RW, xx = i - g * RW;
+        float v[4 + 2 * N];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; ++j) v[j] = sI[(g * 4 + j) * RW + xx];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float r0 = v[o + N] * pc.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float s0 = v[o + N - k], s1 = v[o + N + k];
+                const float p = s0 + s1;
+                r0 = fmaf(pc.g[k], p, r0);
+                r1 = fmaf(pc.xg[k], s1 - s0, r1);
+                r2 = fmaf(pc.xxg[k], p, r2);
+            }
+            const int a = (g * 4 + o) * RWP + xx;
+            sr[a] = r0;
+            sr[P0_TY * RWP + a] = r1;
+            sr[2 * P0_TY * RWP + a] = r2;
+        }
+    }
+    __syncthreads();   // the raw / blurred image is dead from here on: its place becomes the staging tile
+    float4* stQ = reinterpret_cast<float4*>(smem0);          // [P0_TY][QS]
+    float* stS = smem0 + P0_TY * T::QS * 4;                  // [P0_TY][SS]
+    // horizontal pass: 8 outputs per thread; a quarter-warp = 8 rows of one 8-pixel block
+    {
+        const int wi = tid >> 5, lane = tid & 31;
+        const int ty = (wi >> 1) * 8 + (lane & 7), blk = (wi & 1) * 4 + (lane >> 3);
+        if (ty < P0_TY) {
+            const int tx = blk * 8;
+            constexpr int NV = ((8 + 2 * N) + 3) & ~3;
+            float a0[NV], a1[NV], a2[NV];
+#pragma unroll
+            for (int j = 0; j < NV; j += 4) {
+                *reinterpret_cast<float4*>(a0 + j) = *reinterpret_cast<const float4*>(sr + ty * RWP + tx + j);
+                *reinterpret_cast<float4*>(a1 + j) = *reinterpret_cast<const float4*>(sr + P0_TY * RWP + ty * RWP + tx + j);
+                *reinterpret_cast<float4*>(a2 + j) = *reinterpret_cast<const float4*>(sr + 2 * P0_TY * RWP + ty * RWP + tx + j);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float o4[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int c = half * 4 + o + N;
+                    float b1 = a0[c] * pc.g[0], b3 = a1[c] * pc.g[0], b5 = a2[c] * pc.g[0];
+                    float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+#pragma unroll
+                    for (int k = 1; k <= N; ++k) {
+                        const float tg = a0[c + k] + a0[c - k];
+                        b1 = fmaf(tg, pc.g[k], b1);
+                        b4 = fmaf(tg, pc.xxg[k], b4);
+                        b2 = fmaf(a0[c + k] - a0[c - k], pc.xg[k], b2);
+                        b3 = fmaf(a1[c + k] + a1[c - k], pc.g[k], b3);
+                        b6 = fmaf(a1[c + k] - a1[c - k], pc.xg[k], b6);
+                        b5 = fmaf(a2[c + k] + a2[c - k], pc.g[k], b5);
+                    }
+                    stQ[ty * T::QS + tx + half * 4 + o] =
+                        make_float4(b3 * pc.ig11, b2 * pc.ig11, fmaf(b1, pc.ig03, b5 * pc.ig33), fmaf(b1, pc.ig03, b4 * pc.ig33));
+                    o4[o] = b6 * pc.ig55;
+                }
+                *reinterpret_cast<float4*>(stS + ty * T::SS + tx + half * 4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            }
+        }
+    }
+    // generic-proxy writes to shared memory become visible to the bulk-copy engine
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    float4* Rq;
+    float* Rs;
+    r_out(R, imgs_per_array, b, plane, Rq, Rs);
+    const int npx = min(P0_TX, w - x0);   // a multiple of 4 (the launcher checks w % 4 == 0)
+    if ((tid & 31) == 0) {
+        for (int ty = tid >> 5; ty < P0_TY; ty += P0_THREADS / 32) {
+            const int gy = y0 + ty;
+            if (gy >= h) break;
+            const size_t off = static_cast<size_t>(gy) * w + x0;
+            bulk_store(Rq + off, stQ + ty * T::QS, npx * 16);
+            bulk_store(Rs + off, stS + ty * T::SS, npx * 4);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // shared memory must stay intact until the engine has read it
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // F3: flow initialisation of a finer layer = bilinear resize of the coarser flow * mul
 // ------------------------------------------------------------------------------------
 // Source taps and weights come from per-layer tables (up_tables): the fp64 tap arithmetic that
@@ -1507,6 +1743,39 @@ int flow_tile_choice() {
 // finest layer: fused blur + polyexp when the tap count has a compile-time instance
 bool pyr0_polyexp_supported(int poly_n) { return (poly_n == 5 || poly_n == 7) && !getenv("DATMO_NO_PYR0_FUSION"); }
 
+// prev and next frames of the batch in one launch, output through the bulk-copy engine; needs W % 4 == 0
+// and 16-byte aligned frames.  R: the two consecutive R arrays (R0 | R1) of B images each.
+bool pyr0_bulk_supported(const void* prev, const void* next, int dtype, int W, int poly_n) {
+    if (getenv("DATMO_PYR0_LSU")) return false;   // A/B runs against k_pyr0_polyexp
+    const size_t align = dtype == DATMO_U8 ? 4 : 16;
+    return (poly_n == 5 || poly_n == 7) && (W & 3) == 0 && reinterpret_cast<uintptr_t>(prev) % align == 0 &&
+           reinterpret_cast<uintptr_t>(next) % align == 0;
+}
+
+template <typename SrcT, int N>
+int launch_pyr0_bulk_t(datmo_ctx* h, const void* prev, const void* next, int H, int W, int B, float* R,
+                       const PolyCoef& pc) {
+    static SmemGrant grant;
+    DATMO_TRY(datmo_grant_smem(h, k_pyr0_polyexp_t<SrcT, N>, P0T<N>::SMEM, grant));
+    dim3 g(ceil_div(W, P0_TX), ceil_div(H, P0T<N>::TY), 2 * B);
+    {
+        LaunchScope ls(h, DATMO_TAG_POLYEXP);
+        k_pyr0_polyexp_t<SrcT, N><<<g, P0_THREADS, P0T<N>::SMEM, h->stream>>>(
+            static_cast<const SrcT*>(prev), static_cast<const SrcT*>(next), B, R, W, H, B, pc);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+int launch_pyr0_bulk(datmo_ctx* h, const void* prev, const void* next, int dtype, int H, int W, int B, float* R,
+                     const PolyCoef& pc) {
+    if (dtype == DATMO_U8)
+        return pc.n == 5 ? launch_pyr0_bulk_t<uint8_t, 5>(h, prev, next, H, W, B, R, pc)
+                         : launch_pyr0_bulk_t<uint8_t, 7>(h, prev, next, H, W, B, R, pc);
+    return pc.n == 5 ? launch_pyr0_bulk_t<float, 5>(h, prev, next, H, W, B, R, pc)
+                     : launch_pyr0_bulk_t<float, 7>(h, prev, next, H, W, B, R, pc);
+}
+
 int launch_pyr0_polyexp(datmo_ctx* h, const void* img, int dtype, int H, int W, int B, float* R, const PolyCoef& pc) {
     dim3 g(ceil_div(W, P0_TX), ceil_div(H, pc.n <= 5 ? P0Tile<5>::TY : P0Tile<7>::TY), B);
     {
@@ -1730,8 +1999,12 @@ int fb_run_chunk(datmo_ctx* h, const void* prev, const void* next, int dtype, in
         float* R0 = ws.R;
         float* R1 = ws.R + r_array_stride(B, n);
         if (L.k == 0 && L.w == W && L.h == H && pyr0_polyexp_supported(pc.n)) {
-            DATMO_TRY(launch_pyr0_polyexp(h, prev, dtype, H, W, B, R0, pc));
-            DATMO_TRY(launch_pyr0_polyexp(h, next, dtype, H, W, B, R1, pc));
+            if (pyr0_bulk_supported(prev, next, dtype, W, pc.n)) {
+                DATMO_TRY(launch_pyr0_bulk(h, prev, next, dtype, H, W, B, R0, pc));   // R1 follows R0 at r_array_stride
+            } else {
+                DATMO_TRY(launch_pyr0_polyexp(h, prev, dtype, H, W, B, R0, pc));
+                DATMO_TRY(launch_pyr0_polyexp(h, next, dtype, H, W, B, R1, pc));
+            }
         } else {
             if (2 * L.w <= W) {
                 // both frames in one pair of launches: T ([B][H][W] floats) holds 2 B images of width w <= W / 2,

@@ -35,3 +35,26 @@ for size, B in [(400, 1), (800, 1), (1024, 1), (400, 8)]:
     eng.profile(False)
     dev = sum(v["ms"] for v in pr.values()) / n
     print(f"{size}x{size} B={B}: wall {wall:.3f} ms/call, kernels {dev:.3f} ms/call, {(eng.launch_count() - l0) // n} launches/call")
+
+# the same through the C-ABI chain (host frames in, host results out), with its launch train replayed as a
+# CUDA graph and launched plainly
+from datmo_using_optical_flow_b200.engine import HostFlowPipeline  # noqa: E402
+
+for graph in ("1", "0"):
+    os.environ["DATMO_CHAIN_GRAPH"] = graph
+    for size, B in [(400, 1), (1024, 1), (400, 8), (1024, 8)]:
+        a, b = synth.bev_pairs(0, B, size, size)
+        a, b = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+        pipe = HostFlowPipeline(eng, B, size, size, 0.25, 0.25, 0.2, 5.0, 3, farneback_params(), cap=size * size // 2,
+                                max_clusters=1024, n_slots=1, want_cells=False)
+        for _ in range(5):
+            pipe.submit(0, a, b)
+            pipe.collect(0)
+        n = 50
+        t0 = time.perf_counter()
+        for _ in range(n):
+            pipe.submit(0, a, b)
+            pipe.collect(0)
+        wall = (time.perf_counter() - t0) / n * 1e3
+        print(f"chain {size}x{size} B={B} graph={graph}: {wall:.3f} ms per submit + collect (summaries only)")
+        pipe.close()
