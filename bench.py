@@ -143,12 +143,13 @@ class ClockSampler:
 def _cpu_worker(args):
     """One worker process: `repeat` passes of the reference's call sequence over one pair; returns
     (seconds, moving cells, per-stage seconds {flow, masks, dbscan, clusters})."""
-    seed, H, W, repeat = args
+    seed, H, W, repeat = args[:4]
+    sparse = len(args) > 4 and args[4]
     import cv2
     cv2.setNumThreads(1)
     from datmo_using_optical_flow_b200 import synth
     from oracle import cluster_np, dbscan_np, reference_port
-    a, b = synth.bev_pair(seed, H, W)
+    a, b = (synth.bev_pair_sparse if sparse else synth.bev_pair)(seed, H, W)
     xr, yr = [-0.05 * W, 0.05 * W], [-0.05 * H, 0.05 * H]
     st = dict(flow=0.0, masks=0.0, dbscan=0.0, clusters=0.0)
     t_all = time.perf_counter()
@@ -189,12 +190,12 @@ def cpu_pool(cores):
     return pool
 
 
-def cpu_pairs_per_sec(H, W, cores, rounds, pool, seed0=0):
+def cpu_pairs_per_sec(H, W, cores, rounds, pool, seed0=0, sparse=False):
     """`cores` worker processes (cv2 single-threaded in each: OpenCV's Farneback does not scale with
     threads, SURVEY.md §6), one pair per worker per round, on an already warm pool;
     returns (pairs/s, wall seconds, mean per-stage seconds per pair)."""
     t0 = time.perf_counter()
-    out = pool.map(_cpu_worker, [(seed0 + i, H, W, rounds) for i in range(cores)])
+    out = pool.map(_cpu_worker, [(seed0 + i, H, W, rounds, sparse) for i in range(cores)])
     wall = time.perf_counter() - t0
     stage = {k: sum(o[2][k] for o in out) / (cores * rounds) for k in out[0][2]}
     return cores * rounds / wall, wall, stage
@@ -458,6 +459,36 @@ def run_ours(args):
     ms_max = float(t.item())
     value = world * B * args.steps / (ms_max / 1e3)
 
+    # ---- a second, mover-realistic workload (~10^4 moving cells per pair): same chain, sparse frames ---------
+    sp_prev_h, sp_next_h = synth.bev_pairs(rank * B, B, H, W, sparse=True)
+    sp_prev, sp_next = torch.from_numpy(sp_prev_h).cuda(), torch.from_numpy(sp_next_h).cuda()
+
+    def sparse_step():
+        return eng.flow_pipeline(sp_prev, sp_next, px, py, ALPHA_CONT, EPS, MIN_SAMPLES, params, cap=args.cap,
+                                 max_clusters=args.max_clusters, keep_flow=False, flow_buf=flow_buf)
+
+    for _ in range(3):
+        sres = sparse_step()
+    barrier()
+    n_sparse = min(args.steps, 10)
+    se0, se1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    se0.record(main_stream)
+    eng.stream.wait_event(se0)
+    for _ in range(n_sparse):
+        sres = sparse_step()
+    main_stream.wait_stream(eng.stream)
+    se1.record(main_stream)
+    barrier()
+    ts = torch.tensor([se0.elapsed_time(se1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    sparse_line = {"workload": "the same chain on mover-realistic frames: 4-10 vehicle-sized rectangles per 1024x1024 pair",
+                   "value": world * B * n_sparse / (float(ts.item()) / 1e3), "unit": UNIT, "steps": n_sparse,
+                   "ms_per_step": float(ts.item()) / n_sparse,
+                   "moving_cells_per_pair": float(sres.n_valid.float().mean().item()),
+                   "clusters_per_pair": float(sres.n_clusters.float().mean().item())}
+    del sp_prev, sp_next
+
     # ---- end to end through the host-buffer API -------------------------------------------------------
     # pinned host uint8 pairs -> H2D -> flow..clusters -> D2H of counts / labels / indices / summaries,
     # every batch, through the C-ABI chain object (HostFlowPipeline is its ctypes caller): copies on the
@@ -572,6 +603,7 @@ def run_ours(args):
                          "whole_pipeline": {"A_bytes_per_pair": A, "achieved_gbs_per_gpu": whole,
                                             "frac": whole / peak}},
             "stage_ms_per_step": stage_ms,
+            "mover_realistic": sparse_line,
             "parity": par,
             "shard_equality": shard_equal,
             "moving_cells_per_pair": float(shard_stats[:, 0].mean()),
@@ -584,6 +616,10 @@ def run_ours(args):
             pool = cpu_pool(cores)      # imports and a tiny pass in every worker: start-up is not timed
             try:
                 v, wall, stage = cpu_pairs_per_sec(H, W, cores, rounds, pool)
+                sv, swall, sstage = cpu_pairs_per_sec(H, W, cores, rounds, pool, sparse=True)
+                sparse_line["cpu_baseline"] = {"value": sv, "unit": UNIT, "cores": cores, "kind": "port",
+                                               "sample": f"{cores * rounds} sparse pairs, {swall:.1f} s wall",
+                                               "stage_s_per_pair": {k: round(x, 4) for k, x in sstage.items()}}
             finally:
                 pool.close()
                 pool.join()

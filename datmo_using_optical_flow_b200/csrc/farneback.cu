@@ -709,6 +709,35 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp(const SrcT* __restr
 //     stores no longer pass through the LSU, where a thread-contiguous 128-byte store costs a
 //     wavefront per lane.
 // ------------------------------------------------------------------------------------
+// Packed f32x2 arithmetic (sm_100: one FFMA2 / FADD2 / FMUL2 issue slot does two IEEE fp32 operations
+// on a 64-bit register pair; every lane of the pair is rounded exactly like the scalar instruction).
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+          "l"(reinterpret_cast<unsigned long long&>(c)));
+    return r;
+}
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+
 template <int N>
 struct P0T {
     static constexpr int TY = P0Tile<N>::TY;
@@ -716,14 +745,18 @@ struct P0T {
     static constexpr int OX = (N + 1 + 3) & ~3;
     static constexpr int NWD = (P0_TX + OX + N + 1 + 3) / 4;
     static constexpr int SWS = NWD * 4 + 4, SHS = RH + 2;
-    static constexpr int RWP = 4 * ((((RW + 3) / 4)) | 1);   // odd number of 16-byte chunks per r row
+    // r arrays of the horizontal pass: (r0, r1) interleaved per pixel, RW float2 = RW / 2 chunks per row (odd:
+    // RW = 74 / 78), and r2 with an odd number of 16-byte chunks per row
+    static constexpr int RWP = 4 * ((((RW + 3) / 4)) | 1);
     static constexpr int QS = P0_TX + 1;                     // staging row stride, float4 (65 chunks)
     static constexpr int SS = P0_TX + 4;                     // staging row stride of the fifth coefficient, floats
     static constexpr int A_FLOATS_IN = SHS * SWS + RH * RW;  // raw + blurred image
     static constexpr int A_FLOATS_OUT = TY * QS * 4 + TY * SS;
     static constexpr int A_FLOATS = ((A_FLOATS_IN > A_FLOATS_OUT ? A_FLOATS_IN : A_FLOATS_OUT) + 3) & ~3;
-    static constexpr size_t SMEM = static_cast<size_t>(A_FLOATS + 3 * TY * RWP) * sizeof(float);
+    static constexpr size_t SMEM = static_cast<size_t>(A_FLOATS + TY * (2 * RW + RWP)) * sizeof(float);
     static_assert(TY % 8 == 0 && (TY / 8) * 2 <= P0_THREADS / 32, "horizontal pass: 8 rows x 4 blocks per warp");
+    static_assert(RW % 2 == 0 && (RW / 2) % 2 == 1 && (OX - N) % 2 == 1 && SWS % 2 == 0,
+                  "column pairs: 8-byte aligned loads, odd chunk strides");
 };
 
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
@@ -743,7 +776,8 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp_t(const SrcT* __res
     extern __shared__ __align__(128) float smem0[];
     float* sS = smem0;                        // [SHS][SWS] raw frame region
     float* sI = smem0 + SHS * SWS;            // [RH][RW] blurred image
-    float* sr = smem0 + T::A_FLOATS;          // [3][P0_TY][RWP]
+    float2* sR01 = reinterpret_cast<float2*>(smem0 + T::A_FLOATS);   // [P0_TY][RW] (r0, r1) per pixel
+    float* sR2 = smem0 + T::A_FLOATS + 2 * P0_TY * RW;                 // [P0_TY][RWP]
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * P0_TX, y0 = blockIdx.y * P0_TY, b = blockIdx.z;
     const int ox = x0 - OX, oy = y0 - N - 1;
@@ -812,20 +846,27 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp_t(const SrcT* __res
     // blurred image at replicate-clamped coordinates (what polyExp's border handling reads)
     const bool no_clamp = x0 - N >= 0 && x0 - N + RW <= w && y0 - N >= 0 && y0 - N + RH <= h;
     if (no_clamp) {
-        constexpr int CH = 4, RPC = (RH + CH - 1) / CH;  // row chunks per column, rows per chunk
-        for (int i = tid; i < CH * RW; i += P0_THREADS) {
-            const int ch = i / RW, xx = i - ch * RW;
+        // two adjacent columns per thread, packed arithmetic; the row pass of a raw row is computed once and
+        // reused by the three blurred rows that read it
+        constexpr int CH = 6, RPC = (RH + CH - 1) / CH;  // row chunks per column pair, rows per chunk
+        const float2 Q = dup2(0.25f), HF = dup2(0.5f);
+        for (int i = tid; i < CH * (RW / 2); i += P0_THREADS) {
+            const int ch = i / (RW / 2), xx = 2 * (i - ch * (RW / 2));
             const int r0 = ch * RPC;
-            const float* c = sS + (r0 + 1) * SWS + (xx + OX - N);   // raw pixel under blurred (r0, xx)
-            float tm = 0.25f * c[-SWS - 1] + 0.5f * c[-SWS] + 0.25f * c[-SWS + 1];
-            float t0 = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
+            // raw pixel left of blurred (r0, xx): an even shared-memory column, so column pairs load as float2
+            const float* c = sS + (r0 + 1) * SWS + (xx + OX - N - 1);
+            auto row_pass = [&](const float* q) {
+                const float2 a = *reinterpret_cast<const float2*>(q), b2 = *reinterpret_cast<const float2*>(q + 2);
+                return fma2(Q, b2, fma2(HF, make_float2(a.y, b2.x), mul2(Q, a)));
+            };
+            float2 tm = row_pass(c - SWS), t0 = row_pass(c);
 #pragma unroll
             for (int k = 0; k < RPC; ++k) {
                 const int yy = r0 + k;
                 if (yy >= RH) break;
                 c += SWS;
-                const float tp = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
-                sI[yy * RW + xx] = 0.25f * tm + 0.5f * t0 + 0.25f * tp;
+                const float2 tp = row_pass(c);
+                *reinterpret_cast<float2*>(sI + yy * RW + xx) = fma2(Q, tp, fma2(HF, t0, mul2(Q, tm)));
                 tm = t0;
                 t0 = tp;
             }
@@ -835,34 +876,34 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp_t(const SrcT* __res
             const int yy = i / RW, xx = i - yy * RW;
             const int gy = min(max(y0 - N + yy, 0), h - 1), gx = min(max(x0 - N + xx, 0), w - 1);
             const float* c = sS + (gy - oy) * SWS + (gx - ox);
-            const float t0 = 0.25f * c[-SWS - 1] + 0.5f * c[-SWS] + 0.25f * c[-SWS + 1];
-            const float t1 = 0.25f * c[-1] + 0.5f * c[0] + 0.25f * c[1];
-            const float t2 = 0.25f * c[SWS - 1] + 0.5f * c[SWS] + 0.25f * c[SWS + 1];
-            sI[i] = 0.25f * t0 + 0.5f * t1 + 0.25f * t2;
+            // the operation order of the packed path above
+            const float t0 = fmaf(0.25f, c[-SWS + 1], fmaf(0.5f, c[-SWS], 0.25f * c[-SWS - 1]));
+            const float t1 = fmaf(0.25f, c[1], fmaf(0.5f, c[0], 0.25f * c[-1]));
+            const float t2 = fmaf(0.25f, c[SWS + 1], fmaf(0.5f, c[SWS], 0.25f * c[SWS - 1]));
+            sI[i] = fmaf(0.25f, t2, fmaf(0.5f, t1, 0.25f * t0));
         }
     }
     __syncthreads();
-    // vertical pass: 4 output rows per item
-    for (int i = tid; i < (P0_TY / 4) * RW; i += P0_THREADS) {
-        const int g = i / RW, xx = i - g * RW;
-        float v[4 + 2 * N];
+    // vertical pass: 4 output rows x 2 adjacent columns per item, packed arithmetic
+    for (int i = tid; i < (P0_TY / 4) * (RW / 2); i += P0_THREADS) {
+        const int g = i / (RW / 2), xx = 2 * (i - g * (RW / 2));
+        float2 v[4 + 2 * N];
 #pragma unroll
-        for (int j = 0; j < 4 + 2 * N; ++j) v[j] = sI[(g * 4 + j) * RW + xx];
+        for (int j = 0; j < 4 + 2 * N; ++j) v[j] = *reinterpret_cast<const float2*>(sI + (g * 4 + j) * RW + xx);
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-            float r0 = v[o + N] * pc.g[0], r1 = 0.f, r2 = 0.f;
+            float2 r0 = mul2(v[o + N], dup2(pc.g[0])), r1 = make_float2(0.f, 0.f), r2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int k = 1; k <= N; ++k) {
-                const float s0 = v[o + N - k], s1 = v[o + N + k];
-                const float p = s0 + s1;
-                r0 = fmaf(pc.g[k], p, r0);
-                r1 = fmaf(pc.xg[k], s1 - s0, r1);
-                r2 = fmaf(pc.xxg[k], p, r2);
+                const float2 s0 = v[o + N - k], s1 = v[o + N + k];
+                const float2 p = add2(s0, s1);
+                r0 = fma2(dup2(pc.g[k]), p, r0);
+                r1 = fma2(dup2(pc.xg[k]), sub2(s1, s0), r1);
+                r2 = fma2(dup2(pc.xxg[k]), p, r2);
             }
-            const int a = (g * 4 + o) * RWP + xx;
-            sr[a] = r0;
-            sr[P0_TY * RWP + a] = r1;
-            sr[2 * P0_TY * RWP + a] = r2;
+            const int row = g * 4 + o;
+            *reinterpret_cast<float4*>(sR01 + row * RW + xx) = make_float4(r0.x, r1.x, r0.y, r1.y);
+            *reinterpret_cast<float2*>(sR2 + row * RWP + xx) = r2;
         }
     }
     __syncthreads();   // the raw / blurred image is dead from here on: its place becomes the staging tile
@@ -874,32 +915,36 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp_t(const SrcT* __res
         const int ty = (wi >> 1) * 8 + (lane & 7), blk = (wi & 1) * 4 + (lane >> 3);
         if (ty < P0_TY) {
             const int tx = blk * 8;
-            constexpr int NV = ((8 + 2 * N) + 3) & ~3;
-            float a0[NV], a1[NV], a2[NV];
+            constexpr int NP = 8 + 2 * N;              // pixels of the window of 8 outputs
+            constexpr int NV = (NP + 3) & ~3;
+            float2 a01[NP];                            // (r0, r1) per pixel
+            float a2[NV];
 #pragma unroll
-            for (int j = 0; j < NV; j += 4) {
-                *reinterpret_cast<float4*>(a0 + j) = *reinterpret_cast<const float4*>(sr + ty * RWP + tx + j);
-                *reinterpret_cast<float4*>(a1 + j) = *reinterpret_cast<const float4*>(sr + P0_TY * RWP + ty * RWP + tx + j);
-                *reinterpret_cast<float4*>(a2 + j) = *reinterpret_cast<const float4*>(sr + 2 * P0_TY * RWP + ty * RWP + tx + j);
+            for (int j = 0; j < NP; j += 2) {
+                const float4 q = *reinterpret_cast<const float4*>(sR01 + ty * RW + tx + j);
+                a01[j] = make_float2(q.x, q.y), a01[j + 1] = make_float2(q.z, q.w);
             }
+#pragma unroll
+            for (int j = 0; j < NV; j += 4)
+                *reinterpret_cast<float4*>(a2 + j) = *reinterpret_cast<const float4*>(sR2 + ty * RWP + tx + j);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float o4[4];
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
                     const int c = half * 4 + o + N;
-                    float b1 = a0[c] * pc.g[0], b3 = a1[c] * pc.g[0], b5 = a2[c] * pc.g[0];
-                    float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+                    float2 b13 = mul2(a01[c], dup2(pc.g[0]));          // (b1, b3)
+                    float2 b26 = make_float2(0.f, 0.f);                // (b2, b6)
+                    float b5 = a2[c] * pc.g[0], b4 = 0.f;
 #pragma unroll
                     for (int k = 1; k <= N; ++k) {
-                        const float tg = a0[c + k] + a0[c - k];
-                        b1 = fmaf(tg, pc.g[k], b1);
-                        b4 = fmaf(tg, pc.xxg[k], b4);
-                        b2 = fmaf(a0[c + k] - a0[c - k], pc.xg[k], b2);
-                        b3 = fmaf(a1[c + k] + a1[c - k], pc.g[k], b3);
-                        b6 = fmaf(a1[c + k] - a1[c - k], pc.xg[k], b6);
+                        const float2 tg = add2(a01[c + k], a01[c - k]);
+                        b13 = fma2(tg, dup2(pc.g[k]), b13);
+                        b26 = fma2(sub2(a01[c + k], a01[c - k]), dup2(pc.xg[k]), b26);
+                        b4 = fmaf(tg.x, pc.xxg[k], b4);
                         b5 = fmaf(a2[c + k] + a2[c - k], pc.g[k], b5);
                     }
+                    const float b1 = b13.x, b3 = b13.y, b2 = b26.x, b6 = b26.y;
                     stQ[ty * T::QS + tx + half * 4 + o] =
                         make_float4(b3 * pc.ig11, b2 * pc.ig11, fmaf(b1, pc.ig03, b5 * pc.ig33), fmaf(b1, pc.ig03, b4 * pc.ig33));
                     o4[o] = b6 * pc.ig55;
