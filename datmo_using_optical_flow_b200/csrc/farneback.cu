@@ -765,8 +765,8 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigne
                  : "memory");
 }
 
-template <typename SrcT, int N>
-__global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp_t(const SrcT* __restrict__ src0,
+template <typename SrcT, int N, int MINB>
+__global__ void __launch_bounds__(P0_THREADS, MINB) k_pyr0_polyexp_t(const SrcT* __restrict__ src0,
                                                                const SrcT* __restrict__ src1, int n0,
                                                                float* __restrict__ R, int w, int h,
                                                                int imgs_per_array, PolyCoef pc) {
@@ -848,10 +848,16 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp_t(const SrcT* __res
     if (no_clamp) {
         // two adjacent columns per thread, packed arithmetic; the row pass of a raw row is computed once and
         // reused by the three blurred rows that read it
-        constexpr int CH = 6, RPC = (RH + CH - 1) / CH;  // row chunks per column pair, rows per chunk
+        constexpr int CH = N <= 5 ? 6 : 4, RPC = (RH + CH - 1) / CH;  // row chunks per column pair, rows per chunk
         const float2 Q = dup2(0.25f), HF = dup2(0.5f);
-        for (int i = tid; i < CH * (RW / 2); i += P0_THREADS) {
-            const int ch = i / (RW / 2), xx = 2 * (i - ch * (RW / 2));
+        // a warp = one row chunk x 32 adjacent column pairs (conflict-free 8-byte accesses); the RW / 2 - 32
+        // pairs left over of all chunks share one more warp
+        constexpr int REST = RW / 2 - 32;
+        static_assert(REST > 0 && CH * REST <= 32 && CH + 1 <= P0_THREADS / 32, "blur: CH warps + one for the rest");
+        const int bw = tid >> 5, bl = tid & 31;
+        const bool b_on = bw < CH || (bw == CH && bl < CH * REST);
+        if (b_on) {
+            const int ch = bw < CH ? bw : bl / REST, xx = 2 * (bw < CH ? bl : 32 + bl % REST);
             const int r0 = ch * RPC;
             // raw pixel left of blurred (r0, xx): an even shared-memory column, so column pairs load as float2
             const float* c = sS + (r0 + 1) * SWS + (xx + OX - N - 1);
@@ -884,9 +890,13 @@ __global__ void __launch_bounds__(P0_THREADS) k_pyr0_polyexp_t(const SrcT* __res
         }
     }
     __syncthreads();
-    // vertical pass: 4 output rows x 2 adjacent columns per item, packed arithmetic
-    for (int i = tid; i < (P0_TY / 4) * (RW / 2); i += P0_THREADS) {
-        const int g = i / (RW / 2), xx = 2 * (i - g * (RW / 2));
+    // vertical pass: 4 output rows x 2 adjacent columns per item, packed arithmetic; the same warp mapping
+    // (a warp = one group of 4 rows x 32 adjacent column pairs, the rest of all groups in one more warp)
+    constexpr int VG = P0_TY / 4, VREST = RW / 2 - 32;
+    static_assert(VG * VREST <= 32 && VG + 1 <= P0_THREADS / 32, "vertical pass: VG warps + one for the rest");
+    const int vw = tid >> 5, vl = tid & 31;
+    if (vw < VG || (vw == VG && vl < VG * VREST)) {
+        const int g = vw < VG ? vw : vl / VREST, xx = 2 * (vw < VG ? vl : 32 + vl % VREST);
         float2 v[4 + 2 * N];
 #pragma unroll
         for (int j = 0; j < 4 + 2 * N; ++j) v[j] = *reinterpret_cast<const float2*>(sI + (g * 4 + j) * RW + xx);
@@ -1800,12 +1810,19 @@ bool pyr0_bulk_supported(const void* prev, const void* next, int dtype, int W, i
 template <typename SrcT, int N>
 int launch_pyr0_bulk_t(datmo_ctx* h, const void* prev, const void* next, int H, int W, int B, float* R,
                        const PolyCoef& pc) {
-    static SmemGrant grant;
-    DATMO_TRY(datmo_grant_smem(h, k_pyr0_polyexp_t<SrcT, N>, P0T<N>::SMEM, grant));
+    // CTAs per SM the register budget is set for: 4 (64 registers, a few spilled words) against 3 (78)
+    static const int minb = getenv("DATMO_PYR0_MINB") ? atoi(getenv("DATMO_PYR0_MINB")) : (N <= 5 ? 4 : 2);
+    static SmemGrant grant4, grant3;
     dim3 g(ceil_div(W, P0_TX), ceil_div(H, P0T<N>::TY), 2 * B);
-    {
+    if (minb >= 4 && N <= 5) {
+        DATMO_TRY(datmo_grant_smem(h, k_pyr0_polyexp_t<SrcT, N, 4>, P0T<N>::SMEM, grant4));
         LaunchScope ls(h, DATMO_TAG_POLYEXP);
-        k_pyr0_polyexp_t<SrcT, N><<<g, P0_THREADS, P0T<N>::SMEM, h->stream>>>(
+        k_pyr0_polyexp_t<SrcT, N, 4><<<g, P0_THREADS, P0T<N>::SMEM, h->stream>>>(
+            static_cast<const SrcT*>(prev), static_cast<const SrcT*>(next), B, R, W, H, B, pc);
+    } else {
+        DATMO_TRY(datmo_grant_smem(h, k_pyr0_polyexp_t<SrcT, N, 2>, P0T<N>::SMEM, grant3));
+        LaunchScope ls(h, DATMO_TAG_POLYEXP);
+        k_pyr0_polyexp_t<SrcT, N, 2><<<g, P0_THREADS, P0T<N>::SMEM, h->stream>>>(
             static_cast<const SrcT*>(prev), static_cast<const SrcT*>(next), B, R, W, H, B, pc);
     }
     DATMO_POST_LAUNCH(h);
