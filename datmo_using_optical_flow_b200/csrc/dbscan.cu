@@ -13,6 +13,7 @@
 //   border cell   takes the smallest root among its core neighbours, else noise (-1)
 //   label         rank of the root among all roots in ascending order
 // Row-major ranks (the order of np.nonzero) come from a flag scan of the grid.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -570,10 +571,12 @@ __global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__
                                                        const int32_t* __restrict__ indices, int max_clusters,
                                                        unsigned long long* __restrict__ acc,
                                                        unsigned long long* __restrict__ extra) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const int n = min(n_valid[b], cap);
-    if (static_cast<int>(blockIdx.x * blockDim.x) >= n) return;  // whole CTA past the end
+    // grid-stride over the frame's cells: the grid is sized for a typical frame, not for `cap` (a CTA per 256
+    // cells of cap = 512 k launched 65 k CTAs per 32 frames, two thirds of them empty)
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
     int lab = -1;
     unsigned r = 0, c = 0;
     double fvx = 0.0, fvy = 0.0;
@@ -618,6 +621,7 @@ __global__ void __launch_bounds__(256) k_cluster_accum(const float* __restrict__
         atomicAdd(a + 5, srr);
         atomicAdd(a + 6, src);
         atomicAdd(a + 7, scc);
+    }
     }
 }
 
@@ -765,7 +769,7 @@ extern "C" int datmo_cluster_summary_dev(datmo_handle_t h, const float* vx_f, co
     DATMO_CHECK_CUDA(h, cudaMemsetAsync(extra, 0, total * 4 * sizeof(unsigned long long), h->stream));
     {
         LaunchScope ls(h, DATMO_TAG_CLUSTER);
-        dim3 g(ceil_div(cap, 256), batch);
+        dim3 g(std::max(1, std::min(ceil_div(cap, 256), ceil_div(16 * h->sm_count, batch))), batch);
         k_cluster_accum<<<g, 256, 0, h->stream>>>(vx_f, vy_f, H, W, cap, n_valid, labels, indices, max_clusters,
                                                   reinterpret_cast<unsigned long long*>(summary), extra);
     }

@@ -20,6 +20,8 @@
 //   k_ransac_mask   inlier mask of the winner + moments for the refit
 #include <math.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -122,18 +124,25 @@ __device__ __forceinline__ double plane_dist(double a, double b, double c, doubl
 }
 
 // grid: (point tiles, hypothesis groups).  part_*: [n_tiles][iters]
+// list / n_list: when given, thread slot s scores hypothesis list[s] (s < *n_list) and the partials are
+// indexed by slot — the exact pass over the candidates the f32 bounds left (k_ransac_bounds)
 template <int LAYOUT>
 __global__ void __launch_bounds__(RS_THREADS) k_ransac_score(const void* __restrict__ pts, int64_t n, int flip_x,
                                                              const double* __restrict__ planes, int iters, double thr,
                                                              int32_t* __restrict__ part_cnt,
-                                                             double* __restrict__ part_err) {
+                                                             double* __restrict__ part_err,
+                                                             const int32_t* __restrict__ list,
+                                                             const int32_t* __restrict__ n_list) {
     __shared__ double sx[RS_TILE], sy[RS_TILE], sz[RS_TILE];
+    const int n_slots = list ? min(*n_list, iters) : iters;
+    if (static_cast<int>(blockIdx.y) * RS_THREADS >= n_slots) return;   // whole CTA past the candidates
     const int64_t p0 = static_cast<int64_t>(blockIdx.x) * RS_TILE;
     const int np = static_cast<int>(min(static_cast<int64_t>(RS_TILE), n - p0));
     for (int i = threadIdx.x; i < np; i += RS_THREADS) load_point<LAYOUT>(pts, p0 + i, flip_x, sx[i], sy[i], sz[i]);
     __syncthreads();
-    const int hyp = blockIdx.y * RS_THREADS + threadIdx.x;
-    if (hyp >= iters) return;
+    const int slot = blockIdx.y * RS_THREADS + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int hyp = list ? list[slot] : slot;
     const double a = planes[4 * hyp], b = planes[4 * hyp + 1], c = planes[4 * hyp + 2], d = planes[4 * hyp + 3];
     int cnt = 0;
     double err = 0.0;
@@ -147,8 +156,112 @@ __global__ void __launch_bounds__(RS_THREADS) k_ransac_score(const void* __restr
             }
         }
     }
-    part_cnt[static_cast<size_t>(blockIdx.x) * iters + hyp] = cnt;
-    part_err[static_cast<size_t>(blockIdx.x) * iters + hyp] = err;
+    part_cnt[static_cast<size_t>(blockIdx.x) * iters + slot] = cnt;
+    part_err[static_cast<size_t>(blockIdx.x) * iters + slot] = err;
+}
+
+// ---- f32 bounds on every hypothesis' inlier count -------------------------------------------------
+// The exact score needs an fp64 distance per (hypothesis, point) — 1.2e9 of them for a 240 k-point sweep.
+// But RANSAC only needs the WINNER exactly.  In f32, |a x + b y + c z + d| is off by at most
+// 4.5 * 2^-24 * (|x| + |y| + |z| + |d|) (coefficients rounded once, three fused multiply-adds), so counting
+// the points below thr - g and below thr + g, g = 8 * 2^-24 * (max_i (|x| + |y| + |z|) + |d|), brackets the
+// exact count: lo <= count <= hi.  The winner's exact count is at least every other hypothesis' lo, so
+// only hypotheses with hi >= max lo can win; those — a handful on a scene with a ground plane — are
+// re-scored exactly.  Winner, tie-breaks, plane and mask are those of the full fp64 pass.
+__global__ void __launch_bounds__(256) k_ransac_extent(const float4* __restrict__ pts, int64_t n,
+                                                       unsigned* __restrict__ smax_bits) {
+    float m = 0.f;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 p = pts[i];
+        const float v = fabsf(p.x) + fabsf(p.y) + fabsf(p.z);
+        m = v > m ? v : m;           // a NaN coordinate never raises m: such points are outliers of every plane
+        if (!(v < 3.0e38f)) m = 3.0e38f;   // an infinite / NaN extent disables the bounds (g becomes huge)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(smax_bits, __float_as_uint(m));   // non-negative floats order like their bits
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_ransac_bounds(const float4* __restrict__ pts, int64_t n, int flip_x,
+                                                              const double* __restrict__ planes, int iters, double thr,
+                                                              const unsigned* __restrict__ smax_bits,
+                                                              int32_t* __restrict__ part_lo,
+                                                              int32_t* __restrict__ part_hi) {
+    __shared__ float sx[RS_TILE], sy[RS_TILE], sz[RS_TILE];
+    const int64_t p0 = static_cast<int64_t>(blockIdx.x) * RS_TILE;
+    const int np = static_cast<int>(min(static_cast<int64_t>(RS_TILE), n - p0));
+    for (int i = threadIdx.x; i < np; i += RS_THREADS) {
+        const float4 p = pts[p0 + i];
+        sx[i] = flip_x ? -p.x : p.x, sy[i] = p.y, sz[i] = p.z;
+    }
+    __syncthreads();
+    const int hyp = blockIdx.y * RS_THREADS + threadIdx.x;
+    if (hyp >= iters) return;
+    const double ad = planes[4 * hyp], bd = planes[4 * hyp + 1], cd = planes[4 * hyp + 2], dd = planes[4 * hyp + 3];
+    int lo = 0, hi = 0;
+    if (ad != 0.0 || bd != 0.0 || cd != 0.0 || dd != 0.0) {
+        const float a = static_cast<float>(ad), b = static_cast<float>(bd), c = static_cast<float>(cd),
+                    d = static_cast<float>(dd);
+        const double g = 8.0 * 5.9604644775390625e-08 * (static_cast<double>(__uint_as_float(*smax_bits)) + fabs(dd));
+        // thresholds rounded outwards
+        const float t_lo = __double2float_rd(thr - g), t_hi = __double2float_ru(thr + g);
+#pragma unroll 8
+        for (int i = 0; i < np; ++i) {
+            const float t = fabsf(fmaf(a, sx[i], fmaf(b, sy[i], fmaf(c, sz[i], d))));
+            lo += t < t_lo;
+            hi += t < t_hi;
+        }
+    }
+    part_lo[static_cast<size_t>(blockIdx.x) * iters + hyp] = lo;
+    part_hi[static_cast<size_t>(blockIdx.x) * iters + hyp] = hi;
+}
+
+// per-hypothesis bounds, and the largest lower bound
+__global__ void __launch_bounds__(256) k_ransac_bounds_reduce(const int32_t* __restrict__ part_lo,
+                                                              const int32_t* __restrict__ part_hi, int n_tiles, int iters,
+                                                              int32_t* __restrict__ hi, int32_t* __restrict__ lo_max) {
+    const int hyp = blockIdx.x * blockDim.x + threadIdx.x;
+    int l = 0, u = 0;
+    if (hyp < iters) {
+        for (int t = 0; t < n_tiles; ++t) {
+            l += part_lo[static_cast<size_t>(t) * iters + hyp];
+            u += part_hi[static_cast<size_t>(t) * iters + hyp];
+        }
+        hi[hyp] = u;
+    }
+    l = __reduce_max_sync(0xffffffffu, l);
+    if ((threadIdx.x & 31) == 0) atomicMax(lo_max, l);
+}
+
+// candidates: every hypothesis whose upper bound reaches the largest lower bound (any order)
+__global__ void __launch_bounds__(256) k_ransac_candidates(const int32_t* __restrict__ hi, const int32_t* __restrict__ lo_max,
+                                                           int iters, int32_t* __restrict__ list,
+                                                           int32_t* __restrict__ n_list, int32_t* __restrict__ cnt,
+                                                           double* __restrict__ err) {
+    const int hyp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hyp >= iters) return;
+    cnt[hyp] = 0;      // a hypothesis that cannot win takes no part in the arg-max
+    err[hyp] = 0.0;
+    if (hi[hyp] > 0 && hi[hyp] >= *lo_max) list[atomicAdd(n_list, 1)] = hyp;
+}
+
+// exact partials of the candidates (indexed by slot) -> cnt / err of their hypotheses
+__global__ void __launch_bounds__(256) k_ransac_reduce_list(const int32_t* __restrict__ part_cnt,
+                                                            const double* __restrict__ part_err, int n_tiles, int iters,
+                                                            const int32_t* __restrict__ list,
+                                                            const int32_t* __restrict__ n_list, int32_t* __restrict__ cnt,
+                                                            double* __restrict__ err) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= min(*n_list, iters)) return;
+    int c = 0;
+    double e = 0.0;
+    for (int t = 0; t < n_tiles; ++t) {
+        c += part_cnt[static_cast<size_t>(t) * iters + slot];
+        e += part_err[static_cast<size_t>(t) * iters + slot];
+    }
+    cnt[list[slot]] = c;
+    err[list[slot]] = e;
 }
 
 __global__ void __launch_bounds__(256) k_ransac_reduce(const int32_t* __restrict__ part_cnt,
@@ -263,6 +376,10 @@ struct RsWs {
     int32_t* cnt;
     double* err;
     double* mom;
+    int32_t* part_hi;   // f32 bounds pass
+    int32_t* hi;
+    int32_t* list;
+    int32_t* scalars;   // [0] max lower bound, [1] candidate count, [2] bits of max |x|+|y|+|z|
 };
 
 size_t rs_carve(Bump& bump, RsWs& ws, int64_t n, int iters) {
@@ -273,6 +390,10 @@ size_t rs_carve(Bump& bump, RsWs& ws, int64_t n, int iters) {
     ws.cnt = bump.take<int32_t>(iters);
     ws.err = bump.take<double>(iters);
     ws.mom = bump.take<double>(16);
+    ws.part_hi = bump.take<int32_t>(n_tiles * iters);
+    ws.hi = bump.take<int32_t>(iters);
+    ws.list = bump.take<int32_t>(iters);
+    ws.scalars = bump.take<int32_t>(4);
     return bump.off;
 }
 
@@ -292,18 +413,60 @@ int rs_run(datmo_ctx* h, const void* pts, int64_t n, int flip_x, double thr, int
         k_ransac_hyp<LAYOUT><<<ceil_div(iters, 128), 128, 0, h->stream>>>(pts, n, flip_x, ransac_n, iters, seed, planes);
     }
     DATMO_POST_LAUNCH(h);
-    {
-        LaunchScope ls(h, DATMO_TAG_RANSAC);
-        dim3 g(n_tiles, ceil_div(iters, RS_THREADS));
-        k_ransac_score<LAYOUT><<<g, RS_THREADS, 0, h->stream>>>(pts, n, flip_x, planes, iters, thr, ws.part_cnt,
-                                                                ws.part_err);
+    const dim3 g_score(n_tiles, ceil_div(iters, RS_THREADS));
+    // the f32 bounds pass needs float points and is only worth it when nobody asked for every hypothesis' score
+    const bool bounded = LAYOUT == DATMO_PTS_F32_XYZW && !hyp_count && !hyp_err && iters >= 2 * RS_THREADS &&
+                         !getenv("DATMO_RANSAC_EXACT");
+    if (bounded) {
+        const float4* p4 = static_cast<const float4*>(pts);
+        unsigned* smax = reinterpret_cast<unsigned*>(ws.scalars + 2);
+        DATMO_CHECK_CUDA(h, cudaMemsetAsync(ws.scalars, 0, 4 * sizeof(int32_t), h->stream));
+        {
+            LaunchScope ls(h, DATMO_TAG_RANSAC);
+            int64_t blocks = ceil_div64(n, 1024);
+            k_ransac_extent<<<static_cast<int>(blocks > h->sm_count * 4 ? h->sm_count * 4 : blocks), 256, 0, h->stream>>>(p4, n, smax);
+        }
+        DATMO_POST_LAUNCH(h);
+        {
+            LaunchScope ls(h, DATMO_TAG_RANSAC);
+            k_ransac_bounds<<<g_score, RS_THREADS, 0, h->stream>>>(p4, n, flip_x, planes, iters, thr, smax, ws.part_cnt, ws.part_hi);
+        }
+        DATMO_POST_LAUNCH(h);
+        {
+            LaunchScope ls(h, DATMO_TAG_RANSAC);
+            k_ransac_bounds_reduce<<<ceil_div(iters, 256), 256, 0, h->stream>>>(ws.part_cnt, ws.part_hi, n_tiles, iters, ws.hi, ws.scalars);
+        }
+        DATMO_POST_LAUNCH(h);
+        {
+            LaunchScope ls(h, DATMO_TAG_RANSAC);
+            k_ransac_candidates<<<ceil_div(iters, 256), 256, 0, h->stream>>>(ws.hi, ws.scalars, iters, ws.list, ws.scalars + 1, cnt, err);
+        }
+        DATMO_POST_LAUNCH(h);
+        {
+            LaunchScope ls(h, DATMO_TAG_RANSAC);
+            k_ransac_score<LAYOUT><<<g_score, RS_THREADS, 0, h->stream>>>(pts, n, flip_x, planes, iters, thr, ws.part_cnt,
+                                                                          ws.part_err, ws.list, ws.scalars + 1);
+        }
+        DATMO_POST_LAUNCH(h);
+        {
+            LaunchScope ls(h, DATMO_TAG_RANSAC);
+            k_ransac_reduce_list<<<ceil_div(iters, 256), 256, 0, h->stream>>>(ws.part_cnt, ws.part_err, n_tiles, iters, ws.list,
+                                                                              ws.scalars + 1, cnt, err);
+        }
+        DATMO_POST_LAUNCH(h);
+    } else {
+        {
+            LaunchScope ls(h, DATMO_TAG_RANSAC);
+            k_ransac_score<LAYOUT><<<g_score, RS_THREADS, 0, h->stream>>>(pts, n, flip_x, planes, iters, thr, ws.part_cnt,
+                                                                          ws.part_err, nullptr, nullptr);
+        }
+        DATMO_POST_LAUNCH(h);
+        {
+            LaunchScope ls(h, DATMO_TAG_RANSAC);
+            k_ransac_reduce<<<ceil_div(iters, 256), 256, 0, h->stream>>>(ws.part_cnt, ws.part_err, n_tiles, iters, cnt, err);
+        }
+        DATMO_POST_LAUNCH(h);
     }
-    DATMO_POST_LAUNCH(h);
-    {
-        LaunchScope ls(h, DATMO_TAG_RANSAC);
-        k_ransac_reduce<<<ceil_div(iters, 256), 256, 0, h->stream>>>(ws.part_cnt, ws.part_err, n_tiles, iters, cnt, err);
-    }
-    DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, DATMO_TAG_RANSAC);
         k_ransac_best<<<1, 1024, 0, h->stream>>>(cnt, err, planes, iters, best, plane);

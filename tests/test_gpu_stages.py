@@ -289,6 +289,24 @@ def test_ransac_hypotheses_and_scores_vs_oracle(engine):
     assert np.degrees(np.arccos(np.clip(nrm[2], -1, 1))) < 0.5 and abs(abs(refit[3]) - 2.5) < 0.05
 
 
+@pytest.mark.parametrize("flip", [False, True])
+def test_ransac_f32_bounds_pass_picks_the_exact_winner(engine, monkeypatch, flip):
+    """The production path brackets every hypothesis' inlier count in f32 and re-scores only the possible
+    winners in fp64; winner, count, plane, refit and inlier mask must be those of the full fp64 pass
+    (which the hypothesis-level test above pins to the numpy oracle)."""
+    for seq, n_pts in ((1, 20_000), (4, 120_000)):
+        pts = dev(synth.lidar_sweep(seq, 0, 32, n_pts, 2))
+        fast = engine.ransac_ground(pts, 0.5, 5, 5000, seed=11, flip_x=flip)
+        monkeypatch.setenv("DATMO_RANSAC_EXACT", "1")
+        full = engine.ransac_ground(pts, 0.5, 5, 5000, seed=11, flip_x=flip)
+        monkeypatch.delenv("DATMO_RANSAC_EXACT")
+        for k in ("best", "plane", "inlier_mask"):
+            assert np.array_equal(host(fast[k]), host(full[k])), (seq, k)
+        # the refit sums its moments with fp64 atomics: equal up to summation order
+        np.testing.assert_allclose(host(fast["refit"]), host(full["refit"]), rtol=1e-10, atol=1e-12)
+        assert host(fast["best"])[1] > 0.3 * len(pts)        # the ground plane won
+
+
 def test_ransac_f64_layout_and_three_point_model(engine):
     rng = np.random.default_rng(2)
     p = np.column_stack([rng.uniform(-20, 20, 5000), rng.uniform(-20, 20, 5000), 1.0 + rng.normal(0, 0.01, 5000)])
