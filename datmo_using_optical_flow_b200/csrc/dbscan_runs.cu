@@ -30,7 +30,7 @@
 //             row-1 pairs along that column make the union (6 000 runs, 13 000 run pairs that
 //             reach the forest, 300 cell tests per 150 000-cell frame, against 9 million
 //             candidate cell pairs).
-//   flatten   again, marking the roots (= minimum core index of each cluster)
+//   flatten   again (over the head list), marking the roots (= minimum core index of each cluster)
 //   ranks     label of a root = its rank among the roots = sklearn's cluster number
 //   labels    core cell: label of its run's root; border cell: smallest root among the core
 //             cells within eps (the cluster whose DFS reaches it first), else -1
@@ -636,12 +636,15 @@ __global__ void __launch_bounds__(128) k_run_pairs(const float* __restrict__ vx,
 }
 
 // ---- flatten over the head list (between the union passes): one thread per head ---------------------
+// rbits / seg_count (both zeroed by the caller) given: the roots are marked and counted per segment as well
 __global__ void __launch_bounds__(128) k_run_flatten_list(const int32_t* __restrict__ hlist, int hcap,
-                                                          const int32_t* __restrict__ hcount, size_t frame_cells,
-                                                          int32_t* __restrict__ parent) {
+                                                          const int32_t* __restrict__ hcount, RunGeom g,
+                                                          int32_t* __restrict__ parent, uint32_t* __restrict__ rbits,
+                                                          int32_t* __restrict__ seg_count) {
     const int b = blockIdx.y;
     const int n = min(hcount[b], hcap);
-    int32_t* par = parent + static_cast<size_t>(b) * frame_cells;
+    const size_t img = static_cast<size_t>(b) * g.H;
+    int32_t* par = parent + img * g.W;
     const int32_t* list = hlist + static_cast<size_t>(b) * hcap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int a = list[i];
@@ -654,42 +657,11 @@ __global__ void __launch_bounds__(128) k_run_flatten_list(const int32_t* __restr
             __stcg(par + a, up);
             r = up;
         }
-    }
-}
-
-// ---- flatten: heads point at their root; MARK: root bits + per-segment root counts ----------------
-template <bool MARK>
-__global__ void __launch_bounds__(32 * RUN_WARPS) k_run_flatten(const uint32_t* __restrict__ hbits, RunGeom g,
-                                                                int32_t* __restrict__ parent,
-                                                                uint32_t* __restrict__ rbits,
-                                                                int32_t* __restrict__ seg_count) {
-    const WarpPos p = warp_pos(g, g.H);
-    if (!p.live) return;
-    const size_t img = static_cast<size_t>(p.b) * g.H;
-    int32_t* par = parent + img * g.W;
-    const int w = p.wbase + p.lane;
-    uint32_t h = w < g.Ww ? hbits[(img + p.y) * g.Ww + w] : 0u, roots = 0u;
-    while (h) {
-        const int bit = __ffs(h) - 1;
-        h &= h - 1;
-        const int a = p.y * g.W + 32 * w + bit;
-        // every link is finished (previous kernel): roots are fixed points, and concurrent
-        // compressions only replace a parent by one of its ancestors.  Progress is published hop by
-        // hop (pointer jumping): the rows above run first, so a tall region's chains are short by the
-        // time the rows below walk them.
-        int r = __ldcg(par + a);
-        while (true) {
-            const int up = __ldcg(par + r);
-            if (up == r) break;
-            __stcg(par + a, up);
-            r = up;
+        if (rbits != nullptr && r == a) {   // ~150 roots per frame
+            const int y = a / g.W, x = a - y * g.W;
+            atomicOr(rbits + (img + y) * g.Ww + (x >> 5), 1u << (x & 31));
+            atomicAdd(seg_count + (img + y) * g.nseg + (x >> 5) / SEG_WORDS, 1);
         }
-        if (r == a) roots |= 1u << bit;
-    }
-    if (MARK) {
-        if (w < g.Ww) rbits[(img + p.y) * g.Ww + w] = roots;
-        const int cnt = __reduce_add_sync(0xffffffffu, __popc(roots));
-        if (p.lane == 0) seg_count[(img + p.y) * g.nseg + p.seg] = cnt;
     }
 }
 
@@ -857,10 +829,9 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
     DATMO_POST_LAUNCH(h);
     // one thread per run head, grid-stride over the frame's list (its length lives on the device)
     const dim3 grid_list(std::max(16, std::min(64, ceil_div(16 * h->sm_count, batch))), batch);
-    const size_t frame_cells = static_cast<size_t>(H) * W;
     {
         LaunchScope ls(h, tag(3));
-        k_run_flatten_list<<<grid_list, 128, 0, s>>>(hlist, hcap, hcount, frame_cells, parent);
+        k_run_flatten_list<<<grid_list, 128, 0, s>>>(hlist, hcap, hcount, g, parent, nullptr, nullptr);
     }
     DATMO_POST_LAUNCH(h);
     // runs side by side in one row first: regions that touch sideways become one tree before the pass over
@@ -873,7 +844,7 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, tag(3));
-        k_run_flatten_list<<<grid_list, 128, 0, s>>>(hlist, hcap, hcount, frame_cells, parent);
+        k_run_flatten_list<<<grid_list, 128, 0, s>>>(hlist, hcap, hcount, g, parent, nullptr, nullptr);
     }
     DATMO_POST_LAUNCH(h);
     {
@@ -881,9 +852,12 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
         k_run_pairs<<<grid_list, 128, 0, s>>>(vx_f, vy_f, cbits, hbits, ubits, g, eps2, hlist, hcap, hcount, 1, g.r, parent);
     }
     DATMO_POST_LAUNCH(h);
+    // last flatten over the head list; it marks and counts the roots in the (zeroed) root plane
+    DATMO_CHECK_CUDA(h, cudaMemsetAsync(rbits, 0, nw * sizeof(uint32_t), s));
+    DATMO_CHECK_CUDA(h, cudaMemsetAsync(rseg, 0, ns * sizeof(int32_t), s));
     {
         LaunchScope ls(h, tag(3));
-        k_run_flatten<true><<<grid, nt, 0, s>>>(hbits, g, parent, rbits, rseg);
+        k_run_flatten_list<<<grid_list, 128, 0, s>>>(hlist, hcap, hcount, g, parent, rbits, rseg);
     }
     DATMO_POST_LAUNCH(h);
     {
