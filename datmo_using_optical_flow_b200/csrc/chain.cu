@@ -53,7 +53,7 @@ struct datmo_chain {
         int64_t graph_launches = 0;
         int runs = 0;
     };
-    bool use_graph = true;
+    bool use_graph = false;
     std::vector<Slot> slots;
     std::string err;
 };
@@ -304,7 +304,9 @@ int datmo_chain_create(datmo_handle_t h, const datmo_chain_config* cfg, datmo_ch
             cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming) != cudaSuccess)
             return bail("cudaEventCreate failed");
-    c->use_graph = getenv("DATMO_CHAIN_GRAPH") ? atoi(getenv("DATMO_CHAIN_GRAPH")) != 0 : true;
+    // opt-in (DATMO_CHAIN_GRAPH=1): measured, the replayed graph buys nothing — the train is bound by the
+    // kernels' own dependent latencies, not by launch overhead (profiles/r02_latency.txt)
+    c->use_graph = getenv("DATMO_CHAIN_GRAPH") ? atoi(getenv("DATMO_CHAIN_GRAPH")) != 0 : false;
     *out = c;
     return DATMO_OK;
 }
