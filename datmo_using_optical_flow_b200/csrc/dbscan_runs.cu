@@ -160,13 +160,14 @@ __global__ void __launch_bounds__(32 * RUN_WARPS) k_run_pack(const uint8_t* __re
 // ---- scan of the per-segment counts (one CTA per frame), optionally numbering the roots --------
 // counts -> exclusive offsets in place; totals[b] = sum.  With rbits: every root cell's label
 // (its rank among the frame's roots in row-major order) is written to rlabel[cell].
-__global__ void __launch_bounds__(256) k_run_scan(int32_t* __restrict__ seg_count, int nblk, int32_t* __restrict__ totals,
+__global__ void __launch_bounds__(1024) k_run_scan(int32_t* __restrict__ seg_count, int nblk, int32_t* __restrict__ totals,
                                                   const uint32_t* __restrict__ rbits, RunGeom g,
                                                   int32_t* __restrict__ rlabel) {
     const int b = blockIdx.x;
     int32_t* s = seg_count + static_cast<size_t>(b) * nblk;
-    __shared__ int s_part[8];
-    const int per = (nblk + 255) / 256;
+    __shared__ int s_part[32];
+    const int nthr = blockDim.x, nwarp = nthr >> 5;   // a multiple of 32, at most 1024
+    const int per = (nblk + nthr - 1) / nthr;
     const int lo = min(threadIdx.x * per, nblk), hi = min(lo + per, nblk);
     int t = 0;
     for (int i = lo; i < hi; ++i) t += s[i];
@@ -181,8 +182,7 @@ __global__ void __launch_bounds__(256) k_run_scan(int32_t* __restrict__ seg_coun
     if (lane == 31) s_part[wid] = inc;
     __syncthreads();
     int woff = 0, all = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < nwarp; ++i) {
         if (i < wid) woff += s_part[i];
         all += s_part[i];
     }
@@ -361,7 +361,9 @@ __global__ void __launch_bounds__(32 * RUN_WARPS) k_run_heads(const uint32_t* __
                                                               uint32_t* __restrict__ ubits,
                                                               int32_t* __restrict__ parent,
                                                               int32_t* __restrict__ hlist, int hcap,
-                                                              int32_t* __restrict__ hcount) {
+                                                              int32_t* __restrict__ hcount,
+                                                              uint32_t* __restrict__ rbits,
+                                                              int32_t* __restrict__ rseg) {
     const WarpPos p = warp_pos(g, g.H);
     if (!p.live) return;
     const int w = p.wbase + p.lane;
@@ -376,7 +378,9 @@ __global__ void __launch_bounds__(32 * RUN_WARPS) k_run_heads(const uint32_t* __
     if (on) {
         hbits[(img + p.y) * g.Ww + w] = h;
         ubits[(img + p.y) * g.Ww + w] = u;
+        rbits[(img + p.y) * g.Ww + w] = 0u;   // the root plane the last flatten marks (saves two memset launches)
     }
+    if (p.lane == 0) rseg[(img + p.y) * g.nseg + p.seg] = 0;
     // the frame's list of heads (any order): one atomic per warp reserves the slots
     int slot = __popc(h);
 #pragma unroll
@@ -804,6 +808,8 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
     int32_t* hcount = bump.take<int32_t>(batch);
     DATMO_CHECK_CUDA(h, cudaMemsetAsync(hcount, 0, sizeof(int32_t) * batch, h->stream));
     const int nblk = H * g.nseg, nt = 32 * RUN_WARPS;
+    // one CTA per frame scans its segment counts: as many threads as segments, up to 1024 (short serial chains)
+    const int scan_threads = std::min(1024, std::max(256, (nblk + 31) & ~31));
     const dim3 grid(ceil_div(nblk, RUN_WARPS), batch);
     const int vec = (W & 15) == 0 && (reinterpret_cast<uintptr_t>(valid) & 15) == 0;
     cudaStream_t s = h->stream;
@@ -814,7 +820,7 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, tag(0));
-        k_run_scan<<<batch, 256, 0, s>>>(vseg, nblk, n_valid, nullptr, g, nullptr);
+        k_run_scan<<<batch, scan_threads, 0, s>>>(vseg, nblk, n_valid, nullptr, g, nullptr);
     }
     DATMO_POST_LAUNCH(h);
     {
@@ -824,7 +830,7 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, tag(2));
-        k_run_heads<<<grid, nt, 0, s>>>(cbits, pbits, qbits, g, hbits, ubits, parent, hlist, hcap, hcount);
+        k_run_heads<<<grid, nt, 0, s>>>(cbits, pbits, qbits, g, hbits, ubits, parent, hlist, hcap, hcount, rbits, rseg);
     }
     DATMO_POST_LAUNCH(h);
     // one thread per run head, grid-stride over the frame's list (its length lives on the device)
@@ -852,9 +858,7 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
         k_run_pairs<<<grid_list, 128, 0, s>>>(vx_f, vy_f, cbits, hbits, ubits, g, eps2, hlist, hcap, hcount, 1, g.r, parent);
     }
     DATMO_POST_LAUNCH(h);
-    // last flatten over the head list; it marks and counts the roots in the (zeroed) root plane
-    DATMO_CHECK_CUDA(h, cudaMemsetAsync(rbits, 0, nw * sizeof(uint32_t), s));
-    DATMO_CHECK_CUDA(h, cudaMemsetAsync(rseg, 0, ns * sizeof(int32_t), s));
+    // last flatten over the head list; it marks and counts the roots in the root plane (zeroed by k_run_heads)
     {
         LaunchScope ls(h, tag(3));
         k_run_flatten_list<<<grid_list, 128, 0, s>>>(hlist, hcap, hcount, g, parent, rbits, rseg);
@@ -862,7 +866,7 @@ int datmo_dbscan_runs(datmo_ctx* h, char* ws, const float* vx_f, const float* vy
     DATMO_POST_LAUNCH(h);
     {
         LaunchScope ls(h, tag(0));
-        k_run_scan<<<batch, 256, 0, s>>>(rseg, nblk, n_clusters ? n_clusters : ncl, rbits, g, rlabel);
+        k_run_scan<<<batch, scan_threads, 0, s>>>(rseg, nblk, n_clusters ? n_clusters : ncl, rbits, g, rlabel);
     }
     DATMO_POST_LAUNCH(h);
     {

@@ -352,6 +352,103 @@ __global__ void __launch_bounds__(256) k_pyr_h(const SrcT* __restrict__ src0, co
     }
 }
 
+// Horizontal pass for uint8 frames with the lanes of a warp on 32 ROWS of one output column: the tap offset and
+// the blend weight are warp-uniform, the staged rows stay bytes (row stride an odd number of 32-bit words, so the
+// 32 lanes reading one column hit 32 banks — the column-per-lane kernel above strides its lanes by 1 / scale
+// pixels and pays 3 - 4 wavefronts per load on the finer layers, and leaves most of its threads idle on the
+// coarse ones), the taps are immediate operands, and the finished 32 x w block leaves through a transposing tile
+// so the global stores are whole lines.  Same arithmetic, same T.
+constexpr int PH2_ROWS = 32, PH2_THREADS = 256, PH2_MAX_K = 64;
+struct PyrTaps {
+    float k[PH2_MAX_K];
+};
+
+// uint8 -> f32 on the integer and FMA pipes (I2F runs on the quarter-rate conversion unit, and a tap loop that
+// converts every byte it reads is bound by it): 0x4B000000 | b is the float 2^23 + b, exactly
+__device__ __forceinline__ float byte_to_float(unsigned b) { return __uint_as_float(0x4B000000u | b) - 8388608.f; }
+
+template <int KS>   // compile-time tap count; 0 = runtime (ksize_rt)
+__global__ void __launch_bounds__(PH2_THREADS) k_pyr_h_rows(const uint8_t* __restrict__ src0,
+                                                            const uint8_t* __restrict__ src1, int n0,
+                                                            float* __restrict__ T, int H, int W, int w, PyrTaps taps,
+                                                            int ksize_rt, const int* __restrict__ x0tab,
+                                                            const double* __restrict__ ftab, int vec) {
+    extern __shared__ __align__(16) unsigned char sm8[];
+    const int ksize = KS ? KS : ksize_rt;
+    const int r = ksize >> 1, LM = (r + 3) & ~3;
+    const int SWB = 4 * (((LM + W + r + 1 + 3) >> 2) | 1);   // bytes per staged row
+    const int TS = w | 1;                                    // floats per row of the transposing tile
+    unsigned char* sB = sm8;                                                   // [PH2_ROWS][SWB]
+    float* sT = reinterpret_cast<float*>(sm8 + PH2_ROWS * SWB);                // [PH2_ROWS][TS]
+    const int y0 = blockIdx.x * PH2_ROWS, b = blockIdx.y;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    constexpr int NW = PH2_THREADS / 32;
+    const uint8_t* src = (b < n0 ? src0 : src1 - static_cast<size_t>(n0) * H * W) + static_cast<size_t>(b) * H * W;
+    for (int rr = wi; rr < PH2_ROWS; rr += NW) {
+        const uint8_t* grow = src + static_cast<size_t>(min(y0 + rr, H - 1)) * W;
+        unsigned char* srow = sB + rr * SWB + LM;
+        if (vec) {
+            const int per_row = W >> 2;
+#pragma unroll 8
+            for (int j = lane; j < per_row; j += 32)
+                reinterpret_cast<unsigned*>(srow)[j] = __ldg(reinterpret_cast<const unsigned*>(grow) + j);
+            // the reflected margins: r columns on the left, r + 1 on the right
+            for (int m = lane; m < 2 * r + 1; m += 32) {
+                const int c = m < r ? m - r : W + (m - r);
+                srow[c] = grow[reflect101(c, W)];
+            }
+        } else {
+            for (int c = lane - r; c < W + r + 1; c += 32) srow[c] = grow[reflect101(c, W)];
+        }
+    }
+    __syncthreads();
+    const unsigned char* rowp = sB + lane * SWB + LM;
+    float* trow = sT + lane * TS;
+    int xo = wi;
+    int x0n = xo < w ? x0tab[xo] : 0;
+    double fxn = xo < w ? ftab[xo] : 0.0;
+    for (; xo < w; xo += NW) {
+        const unsigned char* s = rowp + x0n;
+        const double fx = fxn;
+        if (xo + NW < w) x0n = x0tab[xo + NW], fxn = ftab[xo + NW];   // the next column's table entries are in flight
+        float a0 = 0.f, a1 = 0.f;
+        if (KS) {
+            float v = byte_to_float(s[0]);
+            a0 = fmaf(taps.k[0], v, a0);
+#pragma unroll
+            for (int q = 1; q < (KS ? KS : 1); ++q) {
+                v = byte_to_float(s[q]);
+                a0 = fmaf(taps.k[q], v, a0);
+                a1 = fmaf(taps.k[q - 1], v, a1);
+            }
+            v = byte_to_float(s[KS]);
+            a1 = fmaf(taps.k[(KS ? KS : 1) - 1], v, a1);
+        } else {
+            float v = byte_to_float(s[0]);
+            float kq = taps.k[0];
+            a0 = fmaf(kq, v, a0);
+            for (int q = 1; q < ksize; ++q) {
+                const float kp = kq;
+                kq = taps.k[q];
+                v = byte_to_float(s[q]);
+                a0 = fmaf(kq, v, a0);
+                a1 = fmaf(kp, v, a1);
+            }
+            v = byte_to_float(s[ksize]);
+            a1 = fmaf(kq, v, a1);
+        }
+        trow[xo] = fx == 0.0 ? a0 : static_cast<float>((1.0 - fx) * a0 + fx * a1);
+    }
+    __syncthreads();
+    for (int rr = wi; rr < PH2_ROWS; rr += NW) {
+        const int y = y0 + rr;
+        if (y >= H) break;
+        float* dst = T + (static_cast<size_t>(b) * H + y) * w;
+        const float* t = sT + rr * TS;
+        for (int x = lane; x < w; x += 32) dst[x] = t[x];
+    }
+}
+
 // Vertical pass: a thread owns an output column and PYR_VROWS consecutive output rows whose tap
 // chains are independent, so their loads overlap.
 __global__ void __launch_bounds__(128) k_pyr_v(const float* __restrict__ T, float* __restrict__ out, int H, int w,
@@ -389,6 +486,85 @@ __global__ void __launch_bounds__(128) k_pyr_v(const float* __restrict__ T, floa
         const int yo = yo0 + rr;
         if (yo < h) {
             const double fy = ftab[yo];
+            out[(static_cast<size_t>(b) * h + yo) * w + xo] =
+                fy == 0.0 ? a0[rr] : static_cast<float>((1.0 - fy) * a0[rr] + fy * a1[rr]);
+        }
+    }
+}
+
+// The same pass with the taps as immediate operands, 32-bit in-image offsets and the border rows decided once per
+// CTA (the four output rows of a CTA are the same for all its threads): k_pyr_v spends ~250 instructions per output
+// on 64-bit address arithmetic, per-load reflection tests and tap loads.  Same arithmetic, same result.
+template <int KS>   // compile-time tap count; 0 = runtime (ksize_rt)
+__global__ void __launch_bounds__(128) k_pyr_v_taps(const float* __restrict__ T, float* __restrict__ out, int H, int w,
+                                                    int h, PyrTaps taps, int ksize_rt,
+                                                    const int* __restrict__ y0tab, const double* __restrict__ ftab) {
+    const int ksize = KS ? KS : ksize_rt;
+    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yo0 = blockIdx.y * PYR_VROWS, b = blockIdx.z;
+    if (xo >= w) return;
+    const float* base = T + static_cast<size_t>(b) * H * w + xo;
+    int ys[PYR_VROWS];
+#pragma unroll
+    for (int rr = 0; rr < PYR_VROWS; ++rr) ys[rr] = __ldg(y0tab + min(yo0 + rr, h - 1));
+    float a0[PYR_VROWS], a1[PYR_VROWS];
+    if (ys[0] >= 0 && ys[PYR_VROWS - 1] + ksize < H) {   // the tables are monotone: every tap row is inside the image
+        const float* p[PYR_VROWS];
+#pragma unroll
+        for (int rr = 0; rr < PYR_VROWS; ++rr) p[rr] = base + ys[rr] * w;
+        if (KS) {
+            float v[PYR_VROWS];
+#pragma unroll
+            for (int rr = 0; rr < PYR_VROWS; ++rr) v[rr] = p[rr][0];
+#pragma unroll
+            for (int rr = 0; rr < PYR_VROWS; ++rr) a0[rr] = fmaf(taps.k[0], v[rr], 0.f), a1[rr] = 0.f;
+#pragma unroll
+            for (int q = 1; q < (KS ? KS : 1); ++q) {
+#pragma unroll
+                for (int rr = 0; rr < PYR_VROWS; ++rr) v[rr] = p[rr][q * w];
+#pragma unroll
+                for (int rr = 0; rr < PYR_VROWS; ++rr) {
+                    a0[rr] = fmaf(taps.k[q], v[rr], a0[rr]);
+                    a1[rr] = fmaf(taps.k[q - 1], v[rr], a1[rr]);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < PYR_VROWS; ++rr) a1[rr] = fmaf(taps.k[(KS ? KS : 1) - 1], p[rr][KS * w], a1[rr]);
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < PYR_VROWS; ++rr) a0[rr] = 0.f, a1[rr] = 0.f;
+            float kp = 0.f;
+            for (int q = 0; q <= ksize; ++q) {
+                const float kq = q < ksize ? taps.k[q] : 0.f;
+#pragma unroll
+                for (int rr = 0; rr < PYR_VROWS; ++rr) {
+                    const float v = p[rr][q * w];
+                    if (q < ksize) a0[rr] = fmaf(kq, v, a0[rr]);
+                    if (q > 0) a1[rr] = fmaf(kp, v, a1[rr]);
+                }
+                kp = kq;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int rr = 0; rr < PYR_VROWS; ++rr) a0[rr] = 0.f, a1[rr] = 0.f;
+        float kp = 0.f;
+        for (int q = 0; q <= ksize; ++q) {
+            const float kq = q < ksize ? taps.k[q] : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < PYR_VROWS; ++rr) {
+                const float v = base[reflect101(ys[rr] + q, H) * w];
+                if (q < ksize) a0[rr] = fmaf(kq, v, a0[rr]);
+                if (q > 0) a1[rr] = fmaf(kp, v, a1[rr]);
+            }
+            kp = kq;
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < PYR_VROWS; ++rr) {
+        const int yo = yo0 + rr;
+        if (yo < h) {
+            const double fy = __ldg(ftab + yo);
             out[(static_cast<size_t>(b) * h + yo) * w + xo] =
                 fy == 0.0 ? a0[rr] : static_cast<float>((1.0 - fy) * a0[rr] + fy * a1[rr]);
         }
@@ -765,7 +941,7 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigne
                  : "memory");
 }
 
-template <typename SrcT, int N, int MINB>
+template <typename SrcT, int N, int MINB, bool BLUR = true>
 __global__ void __launch_bounds__(P0_THREADS, MINB) k_pyr0_polyexp_t(const SrcT* __restrict__ src0,
                                                                const SrcT* __restrict__ src1, int n0,
                                                                float* __restrict__ R, int w, int h,
@@ -785,6 +961,16 @@ __global__ void __launch_bounds__(P0_THREADS, MINB) k_pyr0_polyexp_t(const SrcT*
     // images 0 .. n0-1 come from src0, the rest from src1 (prev and next frames in one launch)
     const SrcT* sb = (b < n0 ? src0 + b * plane : src1 + (b - n0) * plane);
     constexpr int TRIPS = (SHS * NWD + P0_THREADS - 1) / P0_THREADS;
+    if (!BLUR) {
+        // coarse layers: src already is the pyramid image (f32, any width); replicate-clamped copy
+        const float* ib = reinterpret_cast<const float*>(sb);
+#pragma unroll 5
+        for (int i = tid; i < RH * RW; i += P0_THREADS) {
+            const int yy = i / RW, xx = i - yy * RW;
+            const int gy = min(max(y0 - N + yy, 0), h - 1), gx = min(max(x0 - N + xx, 0), w - 1);
+            sI[i] = __ldg(ib + static_cast<size_t>(gy) * w + gx);
+        }
+    } else {
     if (ox >= 0 && ox + NWD * 4 <= w && oy >= 0 && oy + SHS <= h) {
         float4 v[TRIPS];
 #pragma unroll
@@ -889,6 +1075,7 @@ __global__ void __launch_bounds__(P0_THREADS, MINB) k_pyr0_polyexp_t(const SrcT*
             sI[i] = fmaf(0.25f, t2, fmaf(0.5f, t1, 0.25f * t0));
         }
     }
+    }   // BLUR
     __syncthreads();
     // vertical pass: 4 output rows x 2 adjacent columns per item, packed arithmetic; the same warp mapping
     // (a warp = one group of 4 rows x 32 adjacent column pairs, the rest of all groups in one more warp)
@@ -969,19 +1156,28 @@ __global__ void __launch_bounds__(P0_THREADS, MINB) k_pyr0_polyexp_t(const SrcT*
     float4* Rq;
     float* Rs;
     r_out(R, imgs_per_array, b, plane, Rq, Rs);
-    const int npx = min(P0_TX, w - x0);   // a multiple of 4 (the launcher checks w % 4 == 0)
+    const int npx = min(P0_TX, w - x0);
+    // rows of the fifth coefficient start 16-byte aligned only when w % 4 == 0 (always, with BLUR: the launcher
+    // checks); otherwise they leave through the LSU
+    const bool s_bulk = BLUR || (w & 3) == 0;
     if ((tid & 31) == 0) {
         for (int ty = tid >> 5; ty < P0_TY; ty += P0_THREADS / 32) {
             const int gy = y0 + ty;
             if (gy >= h) break;
             const size_t off = static_cast<size_t>(gy) * w + x0;
             bulk_store(Rq + off, stQ + ty * T::QS, npx * 16);
-            bulk_store(Rs + off, stS + ty * T::SS, npx * 4);
+            if (s_bulk) bulk_store(Rs + off, stS + ty * T::SS, npx * 4);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        // shared memory must stay intact until the engine has read it
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    if (!s_bulk) {
+        for (int i = tid; i < P0_TY * P0_TX; i += P0_THREADS) {
+            const int ty = i / P0_TX, tx = i - ty * P0_TX;
+            if (y0 + ty < h && tx < npx) Rs[static_cast<size_t>(y0 + ty) * w + x0 + tx] = stS[ty * T::SS + tx];
+        }
+    }
+    // shared memory must stay intact until the engine has read it
+    if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------
@@ -1748,6 +1944,32 @@ int launch_pyr(datmo_ctx* h, const void* img, const void* img1, int dtype, int H
     DATMO_REQUIRE(h, smem <= 227 * 1024, "image too wide for the pyramid row staging");
     static SmemGrant grant_u8, grant_f32;
     const int nimg = img1 ? 2 * B : B;
+    static const bool h_cols = getenv("DATMO_PYR_H_COLS") != nullptr;   // A/B runs against k_pyr_h
+    const size_t smem_rows = static_cast<size_t>(PH2_ROWS) * 4 * (((((pr + 3) & ~3) + W + pr + 1 + 3) >> 2) | 1) +
+                             static_cast<size_t>(PH2_ROWS) * (L.w | 1) * sizeof(float);
+    PyrTaps taps;
+    {
+        const std::vector<float> g = gaussian_kernel(L.ksize, L.sigma);
+        for (int i = 0; i < PH2_MAX_K; ++i) taps.k[i] = i < L.ksize ? g[i] : 0.f;
+    }
+    if (dtype == DATMO_U8 && !h_cols && L.ksize <= PH2_MAX_K && smem_rows <= 200 * 1024) {
+        const int vec4 = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(img1) & 3) == 0;
+        dim3 g1(ceil_div(H, PH2_ROWS), nimg);
+        static SmemGrant grant7, grant25, grant0;
+        auto go = [&](auto kern, SmemGrant& grant) -> int {
+            DATMO_TRY(datmo_grant_smem(h, kern, smem_rows, grant));
+            LaunchScope ls(h, DATMO_TAG_PYRAMID);
+            kern<<<g1, PH2_THREADS, smem_rows, h->stream>>>(static_cast<const uint8_t*>(img),
+                                                            static_cast<const uint8_t*>(img1), B, T, H, W, L.w, taps,
+                                                            L.ksize, hx, hf, vec4);
+            return DATMO_OK;
+        };
+        if (L.ksize == 7) DATMO_TRY(go(k_pyr_h_rows<7>, grant7));
+        else if (L.ksize == 25) DATMO_TRY(go(k_pyr_h_rows<25>, grant25));
+        else DATMO_TRY(go(k_pyr_h_rows<0>, grant0));
+        DATMO_POST_LAUNCH(h);
+    } else {
     dim3 g1(ceil_div(H, PYR_ROWS), nimg);
     const int vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(img1) & 15) == 0;
@@ -1766,10 +1988,36 @@ int launch_pyr(datmo_ctx* h, const void* img, const void* img1, int dtype, int H
         }
     }
     DATMO_POST_LAUNCH(h);
+    }
     dim3 g2(ceil_div(L.w, 128), ceil_div(L.h, PYR_VROWS), nimg);
+    static const bool v_old = getenv("DATMO_PYR_V_OLD") != nullptr;   // A/B runs against k_pyr_v
     {
         LaunchScope ls(h, DATMO_TAG_PYRAMID);
-        k_pyr_v<<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, gk, L.ksize, vy, vf);
+        if (v_old || L.ksize > PH2_MAX_K)
+            k_pyr_v<<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, gk, L.ksize, vy, vf);
+        else if (L.ksize == 7)
+            k_pyr_v_taps<7><<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, taps, L.ksize, vy, vf);
+        else if (L.ksize == 25)
+            k_pyr_v_taps<25><<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, taps, L.ksize, vy, vf);
+        else
+            k_pyr_v_taps<0><<<g2, 128, 0, h->stream>>>(T, out, H, L.w, L.h, taps, L.ksize, vy, vf);
+    }
+    DATMO_POST_LAUNCH(h);
+    return DATMO_OK;
+}
+
+// coarse layers through the finest layer's kernel without its blur stage (packed arithmetic, bulk-copy row stores)
+template <int N>
+int launch_polyexp_t(datmo_ctx* h, const float* I, float* R, int w, int hh, int B, int imgs_per_array,
+                     const PolyCoef& pc) {
+    constexpr int MINB = N <= 5 ? 4 : 2;
+    static SmemGrant grant;
+    DATMO_TRY(datmo_grant_smem(h, k_pyr0_polyexp_t<float, N, MINB, false>, P0T<N>::SMEM, grant));
+    dim3 g(ceil_div(w, P0_TX), ceil_div(hh, P0T<N>::TY), B);
+    {
+        LaunchScope ls(h, DATMO_TAG_POLYEXP);
+        k_pyr0_polyexp_t<float, N, MINB, false><<<g, P0_THREADS, P0T<N>::SMEM, h->stream>>>(I, nullptr, B, R, w, hh,
+                                                                                          imgs_per_array, pc);
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
@@ -1777,6 +2025,11 @@ int launch_pyr(datmo_ctx* h, const void* img, const void* img1, int dtype, int H
 
 int launch_polyexp(datmo_ctx* h, const float* I, float* R, int w, int hh, int B, int imgs_per_array,
                    const PolyCoef& pc) {
+    static const bool generic = getenv("DATMO_POLYEXP_GENERIC") != nullptr;   // A/B runs against k_polyexp
+    if (!generic && (reinterpret_cast<uintptr_t>(R) & 15) == 0) {
+        if (pc.n == 5) return launch_polyexp_t<5>(h, I, R, w, hh, B, imgs_per_array, pc);
+        if (pc.n == 7) return launch_polyexp_t<7>(h, I, R, w, hh, B, imgs_per_array, pc);
+    }
     int RW = PE_TX + 2 * pc.n, RH = PE_TY + 2 * pc.n;
     size_t smem = static_cast<size_t>(RH * RW + 3 * PE_TY * RW) * sizeof(float);
     static SmemGrant grant;
@@ -1874,31 +2127,43 @@ int launch_flow_iter_w(datmo_ctx* h, const float* R0, const float* R1, const flo
     return DATMO_OK;
 }
 
-// Segment length for the x-marching kernel: the multiple of 32 columns that minimises
-// (CTA waves, rounded up) x (columns evaluated per segment, lead-in and tail included).
-int xm_pick_segment(int w, int bands, int B, int slots) {
-    int best = 32;
+// Band height and segment length for the x-marching kernel: the pair that minimises
+// (CTA waves, rounded up) x (columns evaluated per segment, lead-in and tail included) x (M rows per band).
+// The finest layer of a large batch runs many waves and wants the tall band (least halo); a coarse layer
+// that fits one wave wants the band height that just fills the CTA slots.
+struct XmPlan {
+    int ty, seg;
+};
+constexpr int XM_TY_TALL = 46, XM_TY_SHORT = 36;
+
+XmPlan xm_plan(int w, int hh, int B, int slots) {
+    static const int ty_env = getenv("DATMO_XM_TY") ? atoi(getenv("DATMO_XM_TY")) : 0;
+    static const int seg_env = getenv("DATMO_XM_SEG") ? atoi(getenv("DATMO_XM_SEG")) : 0;
+    XmPlan best{XM_TY_TALL, 32};
     double best_cost = 1e300;
-    for (int seg = 64; seg <= ((w + 31) & ~31); seg += 32) {
-        const int nseg = ceil_div(w, seg);
-        const double ctas = static_cast<double>(nseg) * bands * B;
-        const double waves = ceil(ctas / slots);
-        const double cost = waves * (seg + 16 + 24);  // + ~24 columns' worth of per-CTA fixed cost
-        if (cost < best_cost - 1e-9) best_cost = cost, best = seg;
+    for (int ty : {XM_TY_TALL, XM_TY_SHORT}) {
+        if (ty_env && ty != ty_env) continue;
+        const int bands = ceil_div(hh, ty);
+        for (int seg = 32; seg <= ((w + 31) & ~31); seg += 32) {
+            if (seg_env > 0 && seg != ((seg_env + 31) & ~31)) continue;
+            const int nseg = ceil_div(w, seg);
+            const double ctas = static_cast<double>(nseg) * bands * B;
+            const double waves = ceil(ctas / slots);
+            // + ~24 columns' worth of per-CTA fixed cost
+            const double cost = waves * (seg + 16 + 24) * (ty + 14);
+            if (cost < best_cost - 1e-9) best_cost = cost, best = XmPlan{ty, seg};
+        }
     }
     return best;
 }
 
 template <typename T>
 int launch_flow_iter_xm(datmo_ctx* h, const float* R0, const float* R1, const float* flow_in, float* flow_out, int w,
-                        int hh, int B, float norm) {
+                        int hh, int B, float norm, int seg) {
     static SmemGrant grant;
     DATMO_TRY(datmo_grant_smem(h, k_flow_iter_xm<T>, T::SMEM, grant));
-    const int bands = ceil_div(hh, T::TY);
-    static const int seg_env = getenv("DATMO_XM_SEG") ? atoi(getenv("DATMO_XM_SEG")) : 0;
-    const int seg = seg_env > 0 ? ((seg_env + 31) & ~31) : xm_pick_segment(w, bands, B, h->sm_count * T::MINB);
     static const int prefetch = getenv("DATMO_XM_PREFETCH") ? atoi(getenv("DATMO_XM_PREFETCH")) : 1;
-    dim3 g(ceil_div(w, seg), bands, B);
+    dim3 g(ceil_div(w, seg), ceil_div(hh, T::TY), B);
     {
         LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
         k_flow_iter_xm<T><<<g, T::NT, T::SMEM, h->stream>>>(R0, R1, reinterpret_cast<const float2*>(flow_in),
@@ -1919,8 +2184,14 @@ int launch_flow_iter(datmo_ctx* h, const float* R0, const float* R1, const float
         // x-marching kernel; DATMO_FI_TILE=0 selects the 64x32 tile kernel it replaced (A/B runs,
         // DESIGN.md §5), which also serves the blur-and-solve-only entry point.
         static const int tile = flow_tile_choice();
-        if (FUSED && tile != 0)
-            return launch_flow_iter_xm<XmTile<46, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm);
+        if (FUSED && tile != 0) {
+            const XmPlan plan = xm_plan(w, hh, B, h->sm_count * 2);
+            if (plan.ty == XM_TY_SHORT)
+                return launch_flow_iter_xm<XmTile<XM_TY_SHORT, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B,
+                                                                              norm, plan.seg);
+            return launch_flow_iter_xm<XmTile<XM_TY_TALL, 320, 2, 2, 2>>(h, R0, R1, flow_in, flow_out, w, hh, B, norm,
+                                                                         plan.seg);
+        }
         return launch_flow_iter_w<64, 32, 256, 2, FUSED>(h, R0, R1, flow_in, Min, flow_out, w, hh, B, norm);
     }
     size_t smem = flow_iter_smem(m);
