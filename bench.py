@@ -337,6 +337,12 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = None
+    if world > 1 and not os.environ.get("DATMO_NO_NUMA_BIND"):
+        # one rank per GPU: staging buffers and copy threads on the GPU's own socket (the N = 1 run keeps
+        # every core for its cpu_baseline leg)
+        from datmo_using_optical_flow_b200.sharding import bind_to_device_numa_node
+        numa = bind_to_device_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout while the communicator comes up; stdout carries
@@ -610,6 +616,8 @@ def run_ours(args):
             "clusters_per_pair": float(shard_stats[:, 1].mean()),
             "cap_truncated": bool(shard_stats[:, 2].any()),
         }
+        if numa is not None:
+            line["host_numa_binding_rank0"] = numa
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             rounds = args.cpu_rounds

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) k_pyr_h(const SrcT* __restrict__ src0, co
 // pixels and pays 3 - 4 wavefronts per load on the finer layers, and leaves most of its threads idle on the
 // coarse ones), the taps are immediate operands, and the finished 32 x w block leaves through a transposing tile
 // so the global stores are whole lines.  Same arithmetic, same T.
-constexpr int PH2_ROWS = 32, PH2_THREADS = 256, PH2_MAX_K = 64;
+constexpr int PH2_ROWS = 32, PH2_THREADS = 512, PH2_MAX_K = 64;   // 16 warps share the staged rows
 struct PyrTaps {
     float k[PH2_MAX_K];
 };
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(PH2_THREADS) k_pyr_h_rows(const uint8_t* __res
     float* sT = reinterpret_cast<float*>(sm8 + PH2_ROWS * SWB);                // [PH2_ROWS][TS]
     const int y0 = blockIdx.x * PH2_ROWS, b = blockIdx.y;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-    constexpr int NW = PH2_THREADS / 32;
+    const int NW = blockDim.x >> 5;
     const uint8_t* src = (b < n0 ? src0 : src1 - static_cast<size_t>(n0) * H * W) + static_cast<size_t>(b) * H * W;
     for (int rr = wi; rr < PH2_ROWS; rr += NW) {
         const uint8_t* grow = src + static_cast<size_t>(min(y0 + rr, H - 1)) * W;
@@ -1956,11 +1956,14 @@ int launch_pyr(datmo_ctx* h, const void* img, const void* img1, int dtype, int H
         const int vec4 = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(img1) & 3) == 0;
         dim3 g1(ceil_div(H, PH2_ROWS), nimg);
+        static const int h_threads =
+            getenv("DATMO_PYR_H_THREADS") ? std::min(PH2_THREADS, std::max(32, atoi(getenv("DATMO_PYR_H_THREADS")) & ~31))
+                                          : PH2_THREADS;
         static SmemGrant grant7, grant25, grant0;
         auto go = [&](auto kern, SmemGrant& grant) -> int {
             DATMO_TRY(datmo_grant_smem(h, kern, smem_rows, grant));
             LaunchScope ls(h, DATMO_TAG_PYRAMID);
-            kern<<<g1, PH2_THREADS, smem_rows, h->stream>>>(static_cast<const uint8_t*>(img),
+            kern<<<g1, h_threads, smem_rows, h->stream>>>(static_cast<const uint8_t*>(img),
                                                             static_cast<const uint8_t*>(img1), B, T, H, W, L.w, taps,
                                                             L.ksize, hx, hf, vec4);
             return DATMO_OK;
@@ -2131,18 +2134,22 @@ int launch_flow_iter_w(datmo_ctx* h, const float* R0, const float* R1, const flo
 // (CTA waves, rounded up) x (columns evaluated per segment, lead-in and tail included) x (M rows per band).
 // The finest layer of a large batch runs many waves and wants the tall band (least halo); a coarse layer
 // that fits one wave wants the band height that just fills the CTA slots.
+// The band height decides where the vertical window sums split their 15-row blocks, i.e. the rounding of the
+// sums, so it must depend on the layer's GEOMETRY only — a pair's flow may not change with the batch it is
+// computed in (tests: batched == single, shard equality).  It is therefore planned for a nominal batch of 32
+// on a 148-SM part; the segment length (no effect on the arithmetic: groups stay aligned to multiples of 32
+// columns) is planned for the actual batch and device.
 struct XmPlan {
     int ty, seg;
 };
 constexpr int XM_TY_TALL = 46, XM_TY_SHORT = 36;
 
-XmPlan xm_plan(int w, int hh, int B, int slots) {
-    static const int ty_env = getenv("DATMO_XM_TY") ? atoi(getenv("DATMO_XM_TY")) : 0;
+XmPlan xm_plan_for(int w, int hh, int B, int slots, int only_ty) {
     static const int seg_env = getenv("DATMO_XM_SEG") ? atoi(getenv("DATMO_XM_SEG")) : 0;
     XmPlan best{XM_TY_TALL, 32};
     double best_cost = 1e300;
     for (int ty : {XM_TY_TALL, XM_TY_SHORT}) {
-        if (ty_env && ty != ty_env) continue;
+        if (only_ty && ty != only_ty) continue;
         const int bands = ceil_div(hh, ty);
         for (int seg = 32; seg <= ((w + 31) & ~31); seg += 32) {
             if (seg_env > 0 && seg != ((seg_env + 31) & ~31)) continue;
@@ -2155,6 +2162,12 @@ XmPlan xm_plan(int w, int hh, int B, int slots) {
         }
     }
     return best;
+}
+
+XmPlan xm_plan(int w, int hh, int B, int slots) {
+    static const int ty_env = getenv("DATMO_XM_TY") ? atoi(getenv("DATMO_XM_TY")) : 0;
+    const int ty = ty_env ? ty_env : xm_plan_for(w, hh, 32, 2 * 148, 0).ty;
+    return xm_plan_for(w, hh, B, slots, ty);
 }
 
 template <typename T>

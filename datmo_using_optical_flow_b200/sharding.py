@@ -28,6 +28,41 @@ def shard_sequences(n_sequences: int, rank: int, world: int) -> list[int]:
     return list(range(start, start + count))
 
 
+def _parse_cpulist(text: str) -> set[int]:
+    """'0-3,8,10-11' -> {0, 1, 2, 3, 8, 10, 11} (the format of /sys/devices/system/node/node*/cpulist)."""
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_device_numa_node(device_index: int, sysfs: str = "/sys") -> dict:
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off, so that the pinned staging
+    buffers it allocates next (first touch) and the copy threads sit on the socket whose PCIe root the GPU
+    uses: with one rank per GPU on a two-socket host, half the ranks otherwise DMA across the socket link.
+    Returns what was done ({"node": n, "cpus": k} or {"node": None, "why": ...}); never raises."""
+    import os
+
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"{sysfs}/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read())
+        if node < 0:
+            return {"node": None, "why": "the platform reports no NUMA node for the GPU"}
+        with open(f"{sysfs}/devices/system/node/node{node}/cpulist") as fh:
+            cpus = _parse_cpulist(fh.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": None, "why": f"no allowed CPU on node {node}"}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception as exc:  # missing sysfs entries, old torch without the pci_* properties, ...
+        return {"node": None, "why": f"{type(exc).__name__}: {exc}"}
+
+
 def _is_dist() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 

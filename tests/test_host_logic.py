@@ -299,3 +299,32 @@ def test_artefact_writers_match_reference_savers(tmp_path, monkeypatch):
     su.save_ekf_tracks(tracks, 4)
     artefacts.save_ekf_tracks(str(ours), tracks, 4)
     assert open(ours / "ekf_tracks_frame_4.yaml").read() == open(theirs / "ekf_tracks_frame_4.yaml").read()
+
+
+def test_numa_binding_reads_sysfs_and_never_raises(tmp_path, monkeypatch):
+    """bind_to_device_numa_node: the GPU's PCI address -> numa_node -> cpulist -> sched_setaffinity; every
+    missing piece degrades to a no-op with a reason."""
+    import os
+    import types
+
+    import torch
+
+    from datmo_using_optical_flow_b200 import sharding
+
+    assert sharding._parse_cpulist("0-2,5,7-8\n") == {0, 1, 2, 5, 7, 8}
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1B, pci_device_id=0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: props)
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    allowed = sorted(os.sched_getaffinity(0))
+    (node / "cpulist").write_text(f"{allowed[0]}\n")
+    called = {}
+    monkeypatch.setattr(os, "sched_setaffinity", lambda pid, cpus: called.update(pid=pid, cpus=set(cpus)))
+    out = sharding.bind_to_device_numa_node(0, sysfs=str(tmp_path))
+    assert out == {"node": 1, "cpus": 1} and called == {"pid": 0, "cpus": {allowed[0]}}
+    (dev / "numa_node").write_text("-1\n")
+    assert sharding.bind_to_device_numa_node(0, sysfs=str(tmp_path))["node"] is None
+    assert sharding.bind_to_device_numa_node(0, sysfs=str(tmp_path / "nowhere"))["node"] is None
