@@ -266,7 +266,7 @@ __host__ __device__ __forceinline__ size_t r_array_stride(int B, size_t n) {
 }
 // image index bz of a launch over several consecutive R arrays of B images each
 __device__ __forceinline__ void r_out(float* R, int B, int bz, size_t n, float4*& q, float*& sdst) {
-    const int arr = bz / B, b = bz - arr * B;
+    const int arr = bz < B ? 0 : (bz < 2 * B ? 1 : bz / B), b = bz - arr * B;   // one or two arrays: no division
     float* base = R + static_cast<size_t>(arr) * r_array_stride(B, n);
     q = reinterpret_cast<float4*>(base) + static_cast<size_t>(b) * n;
     sdst = base + 4 * static_cast<size_t>(B) * n + static_cast<size_t>(b) * n;
@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(P0_THREADS, MINB) k_pyr0_polyexp_t(const SrcT*
             const int i = tid + t * P0_THREADS;
             if (i < SHS * NWD) {
                 const int yy = i / NWD, wd = i - yy * NWD;
-                const SrcT* p = sb + static_cast<size_t>(oy + yy) * w + ox + wd * 4;
+                const SrcT* p = sb + ((oy + yy) * w + ox + wd * 4);   // a frame has fewer than 2^31 pixels
                 if (sizeof(SrcT) == 1) {
                     const uchar4 u = *reinterpret_cast<const uchar4*>(p);
                     v[t] = make_float4(u.x, u.y, u.z, u.w);
@@ -1153,31 +1153,32 @@ __global__ void __launch_bounds__(P0_THREADS, MINB) k_pyr0_polyexp_t(const SrcT*
     // generic-proxy writes to shared memory become visible to the bulk-copy engine
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    float4* Rq;
-    float* Rs;
-    r_out(R, imgs_per_array, b, plane, Rq, Rs);
     const int npx = min(P0_TX, w - x0);
     // rows of the fifth coefficient start 16-byte aligned only when w % 4 == 0 (always, with BLUR: the launcher
     // checks); otherwise they leave through the LSU
     const bool s_bulk = BLUR || (w & 3) == 0;
-    if ((tid & 31) == 0) {
-        for (int ty = tid >> 5; ty < P0_TY; ty += P0_THREADS / 32) {
-            const int gy = y0 + ty;
-            if (gy >= h) break;
-            const size_t off = static_cast<size_t>(gy) * w + x0;
-            bulk_store(Rq + off, stQ + ty * T::QS, npx * 16);
-            if (s_bulk) bulk_store(Rs + off, stS + ty * T::SS, npx * 4);
-        }
+    // lane l of warp v hands row v + 8 l to the copy engine (three lanes per warp issue side by side; one lane
+    // looping over the warp's rows cost 6 % of the kernel's issue slots)
+    const int ty_b = (tid >> 5) + (P0_THREADS / 32) * (tid & 31);
+    const bool mover = ty_b < P0_TY && y0 + ty_b < h;
+    if (!mover && s_bulk) return;
+    float4* Rq;
+    float* Rs;
+    r_out(R, imgs_per_array, b, plane, Rq, Rs);
+    if (mover) {
+        const int off = (y0 + ty_b) * w + x0;
+        bulk_store(Rq + off, stQ + ty_b * T::QS, npx * 16);
+        if (s_bulk) bulk_store(Rs + off, stS + ty_b * T::SS, npx * 4);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (!s_bulk) {
         for (int i = tid; i < P0_TY * P0_TX; i += P0_THREADS) {
             const int ty = i / P0_TX, tx = i - ty * P0_TX;
-            if (y0 + ty < h && tx < npx) Rs[static_cast<size_t>(y0 + ty) * w + x0 + tx] = stS[ty * T::SS + tx];
+            if (y0 + ty < h && tx < npx) Rs[(y0 + ty) * w + x0 + tx] = stS[ty * T::SS + tx];
         }
     }
     // shared memory must stay intact until the engine has read it
-    if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (mover) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------

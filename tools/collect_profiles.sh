@@ -19,10 +19,10 @@ CMD1="python bench.py --steps 1 --warmup 3 --no-cpu --no-parity"
 $CMD1 > $O/r02_plain1.log 2>&1 && \
 ncu --set full --import-source on --clock-control none -k regex:k_flow_iter_xm -s 40 -c 1 -o $O/r02_prof_xm $CMD1 > $O/r02_ncu_xm.log 2>&1
 $CMD1 > $O/r02_plain1.log 2>&1 && \
-ncu --set full --import-source on --clock-control none -k regex:k_pyr0_polyexp_t -s 3 -c 1 -o $O/r02_prof_pyr0 $CMD1 > $O/r02_ncu_pyr0.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:k_pyr0_polyexp_t -s 5 -c 1 -o $O/r02_prof_pyr0 $CMD1 > $O/r02_ncu_pyr0.log 2>&1
 $CMD1 > $O/r02_plain1.log 2>&1 && \
 ncu --section SpeedOfLight --section Occupancy --section WarpStateStats --section MemoryWorkloadAnalysis --clock-control none \
-    -k regex:"k_run_|k_velmask|k_cluster|k_chain|k_pyr_h|k_pyr_v|k_polyexp|k_upsample" -s 60 -c 40 -o $O/r02_prof_small $CMD1 > $O/r02_ncu_small.log 2>&1
+    -k regex:"k_run_|k_velmask|k_cluster|k_chain|k_pyr_h|k_pyr_v|k_pyr0_polyexp_t|k_upsample" -s 69 -c 46 -o $O/r02_prof_small $CMD1 > $O/r02_ncu_small.log 2>&1
 PRE="python tools/preprocess_latency.py"
 $PRE > $O/r02_plain2.log 2>&1 && \
 ncu --section SpeedOfLight --section Occupancy --section WarpStateStats --section MemoryWorkloadAnalysis --clock-control none \

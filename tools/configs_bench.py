@@ -15,7 +15,10 @@ CFG = [("cfg1 400^2 reference params", 400, 64, {}),
        ("cfg2 800^2 pyr 0.5 x 5", 800, 32, dict(pyr_scale=0.5, levels=5)),
        ("cfg3 1024^2 reference params", 1024, 32, {}),
        ("cfg4 2048^2 poly_n 7, sigma 1.5, 10 iterations", 2048, 8, dict(poly_n=7, poly_sigma=1.5, iterations=10))]
+only = os.environ.get("CFG_ONLY")   # e.g. CFG_ONLY=cfg1 (for a launch list of one configuration)
 for name, size, B, kw in CFG:
+    if only and not name.startswith(only):
+        continue
     a, b = synth.bev_pairs(0, B, size, size)
     a, b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     p = farneback_params(**kw)

@@ -27,9 +27,9 @@ if os.environ.get("DATMO_DBSCAN_CELLS"):
     names = {"pyramid": "flag scans (2x3 kernels)", "polyexp": "k_core", "flow_init": "k_link_near",
              "flow_iter": "k_flatten (x3)", "velmask": "k_union_far", "dbscan": "k_union_near", "bev": "k_labels"}
 else:
-    names = {"pyramid": "k_run_pack + 2 x k_run_scan", "polyexp": "k_run_core", "flow_init": "k_run_link",
-             "flow_iter": "k_run_flatten (x2)", "velmask": "k_run_union rows 2..r", "dbscan": "k_run_union rows 0..1",
-             "bev": "k_run_labels"}
+    names = {"pyramid": "k_run_pack + 2 x k_run_scan", "polyexp": "k_run_core", "flow_init": "k_run_heads",
+             "flow_iter": "k_run_flatten_list (x3)", "velmask": "k_run_pairs (row 0, rows 1..r)",
+             "dbscan": "(unused)", "bev": "k_run_labels"}
 tot = 0
 for k, v in p.items():
     if v["launches"]:
