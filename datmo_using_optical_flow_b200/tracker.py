@@ -67,19 +67,30 @@ class TrackManager:
         old = self.tracks
         new: dict[int, Track] = {}
         next_id = max(old.keys(), default=0) + 1
+        # every track's [row, col, 0, 0] as one matrix: a cluster's distances to all tracks are one vector
+        # expression instead of a Python loop (a track updated by an earlier cluster of this frame is seen with
+        # its new state, as in the reference's loop: its row is refreshed after the update)
+        ids = list(old.keys())
+        pos = np.zeros((len(ids), 4))
+        for i, tid in enumerate(ids):
+            pos[i, 0], pos[i, 1] = old[tid].state[0], old[tid].state[1]
         for _, cl in clusters.items():
             feat = np.array([*cl["centroid"], *np.real(cl["eigenvalues"])], dtype=float)
-            best, best_d = None, math.inf
-            for tid, t in old.items():
-                d = float(np.linalg.norm(feat - np.array([t.state[0], t.state[1], 0.0, 0.0])))
-                if d < best_d and d < self.gamma:
-                    best, best_d = tid, d
+            best = None
+            if ids:
+                diff = feat - pos
+                d = np.sqrt((diff * diff).sum(axis=1))
+                d[np.isnan(d)] = np.inf          # a NaN distance never matches (d < best_d is false in the loop form)
+                i = int(np.argmin(d))            # the first of equal minima, like the strict < of the loop
+                if d[i] < self.gamma:
+                    best = ids[i]
             z = np.asarray(cl["measurement"], dtype=float)
             if best is not None:
                 t = old[best]
                 self._predict(t, dt, z[2], z[3])
                 self._update(t, z)
                 new[best] = t
+                pos[i, 0], pos[i, 1] = t.state[0], t.state[1]
             else:
                 new[next_id] = Track(state=z.copy())
         self.tracks = new
