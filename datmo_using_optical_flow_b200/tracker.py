@@ -71,28 +71,31 @@ class TrackManager:
         # expression instead of a Python loop (a track updated by an earlier cluster of this frame is seen with
         # its new state, as in the reference's loop: its row is refreshed after the update)
         ids = list(old.keys())
-        pos = np.zeros((len(ids), 4))
-        for i, tid in enumerate(ids):
-            pos[i, 0], pos[i, 1] = old[tid].state[0], old[tid].state[1]
+        pos = np.array([[t.state[0], t.state[1]] for t in old.values()], dtype=float).reshape(-1, 2)
+        last_new = None      # every unmatched cluster takes the SAME new id: only the last one's track survives
         for _, cl in clusters.items():
-            feat = np.array([*cl["centroid"], *np.real(cl["eigenvalues"])], dtype=float)
+            c, ev = cl["centroid"], np.real(cl["eigenvalues"])
             best = None
             if ids:
-                diff = feat - pos
-                d = np.sqrt((diff * diff).sum(axis=1))
+                # || [centroid, eigenvalues] - [row, col, 0, 0] ||, summed in the order of the 4-vector norm
+                dr, dc = c[0] - pos[:, 0], c[1] - pos[:, 1]
+                d = np.sqrt(dr * dr + dc * dc + ev[0] * ev[0] + ev[1] * ev[1])
                 d[np.isnan(d)] = np.inf          # a NaN distance never matches (d < best_d is false in the loop form)
                 i = int(np.argmin(d))            # the first of equal minima, like the strict < of the loop
                 if d[i] < self.gamma:
                     best = ids[i]
-            z = np.asarray(cl["measurement"], dtype=float)
             if best is not None:
+                z = np.asarray(cl["measurement"], dtype=float)
                 t = old[best]
                 self._predict(t, dt, z[2], z[3])
                 self._update(t, z)
                 new[best] = t
                 pos[i, 0], pos[i, 1] = t.state[0], t.state[1]
             else:
-                new[next_id] = Track(state=z.copy())
+                new.setdefault(next_id, None)    # keeps the position of the first unmatched cluster in the dict
+                last_new = cl["measurement"]
+        if last_new is not None:
+            new[next_id] = Track(state=np.array(last_new, dtype=float))
         self.tracks = new
         return new
 
