@@ -55,6 +55,20 @@ def test_stage_pyramid_image(engine, dtype):
         assert np.abs(got - want).max() <= 3e-4, (L, np.abs(got - want).max())       # 0..255 scale, summation order
 
 
+@pytest.mark.parametrize("H,W,scale,levels", [(333, 501, 0.3, 5), (123, 257, 0.7, 3), (96, 1028, 0.5, 4)])
+def test_stage_pyramid_image_ragged_widths_and_batches(engine, H, W, scale, levels):
+    """uint8 frames whose width is not a multiple of four (byte-wise staging of the rows-per-lane horizontal
+    pass), compile-time (7, 25) and run-time tap counts, several images per call, heights that are not a multiple
+    of the 32 staged rows."""
+    imgs = np.stack([synth.bev_pair(s, H, W)[0] for s in (1, 2, 3)])
+    for L in fb.level_plan(H, W, scale, levels):
+        got = host(engine.fb_pyramid_image(dev(imgs), L["ksize"], L["sigma"], L["h"], L["w"]))
+        assert got.shape == (3, L["h"], L["w"])
+        for b in range(3):
+            want = fb.pyramid_image(imgs[b], L)
+            assert np.abs(got[b] - want).max() <= 3e-4, (L, b, np.abs(got[b] - want).max())
+
+
 @pytest.mark.parametrize("n,sigma", [(5, 5.0), (7, 1.5), (5, 1.1), (3, 0.0)])
 def test_stage_polyexp(engine, n, sigma):
     a, _ = synth.textured_pair(3, 70, 90)
@@ -63,6 +77,19 @@ def test_stage_polyexp(engine, n, sigma):
     got = np.moveaxis(host(engine.fb_polyexp(dev(I), n, sigma))[0], 0, -1)
     scale = np.abs(want).max(axis=(0, 1))
     assert (np.abs(got - want).max(axis=(0, 1)) <= 1e-5 * np.maximum(scale, 1)).all(), np.abs(got - want).max(axis=(0, 1))
+
+
+@pytest.mark.parametrize("H,W", [(70, 90), (61, 131), (24, 64), (200, 307)])
+def test_stage_polyexp_batched_any_width(engine, H, W):
+    """The coarse layers' polynomial expansion (the packed kernel without its blur stage): widths that are and are
+    not multiples of four (fifth coefficient through the copy engine / through the LSU), several images."""
+    imgs = np.stack([synth.textured_pair(s, H, W)[0].astype(np.float32) for s in (3, 4)])
+    got = host(engine.fb_polyexp(dev(imgs), 5, 5.0))
+    for b in range(2):
+        want = fb.poly_exp(imgs[b], 5, 5.0)
+        g = np.moveaxis(got[b], 0, -1)
+        scale = np.abs(want).max(axis=(0, 1))
+        assert (np.abs(g - want).max(axis=(0, 1)) <= 1e-5 * np.maximum(scale, 1)).all(), (b, np.abs(g - want).max(axis=(0, 1)))
 
 
 def _layer_inputs(seed=2, H=80, W=100):
