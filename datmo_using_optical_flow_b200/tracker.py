@@ -67,21 +67,34 @@ class TrackManager:
         old = self.tracks
         new: dict[int, Track] = {}
         next_id = max(old.keys(), default=0) + 1
-        # every track's [row, col, 0, 0] as one matrix: a cluster's distances to all tracks are one vector
-        # expression instead of a Python loop (a track updated by an earlier cluster of this frame is seen with
-        # its new state, as in the reference's loop: its row is refreshed after the update)
+        # every track's (row, col) up front: a cluster's distances to all tracks are one vector expression
+        # (many tracks) or a loop over plain floats (a handful) instead of one numpy norm per (cluster, track).  A
+        # track updated by an earlier cluster of this frame is seen with its new state, as in the reference's
+        # loop: its row is refreshed after the update
         ids = list(old.keys())
-        pos = np.array([[t.state[0], t.state[1]] for t in old.values()], dtype=float).reshape(-1, 2)
+        few = len(ids) <= 8                      # a handful of tracks: plain float arithmetic beats numpy's call overhead
+        pos = [[float(t.state[0]), float(t.state[1])] for t in old.values()]
+        if not few:
+            pos = np.array(pos, dtype=float).reshape(-1, 2)
         last_new = None      # every unmatched cluster takes the SAME new id: only the last one's track survives
         for _, cl in clusters.items():
             c, ev = cl["centroid"], np.real(cl["eigenvalues"])
             best = None
-            if ids:
-                # || [centroid, eigenvalues] - [row, col, 0, 0] ||, summed in the order of the 4-vector norm
+            # || [centroid, eigenvalues] - [row, col, 0, 0] ||, summed in the order of the 4-vector norm; the first
+            # of equal minima wins (the strict < of the reference's loop), a NaN distance never matches
+            if few:
+                c0, c1, e0, e1 = float(c[0]), float(c[1]), float(ev[0]), float(ev[1])
+                best_d = math.inf
+                for k, (pr, pc) in enumerate(pos):
+                    dr, dc = c0 - pr, c1 - pc
+                    d = math.sqrt(dr * dr + dc * dc + e0 * e0 + e1 * e1)
+                    if d < best_d and d < self.gamma:
+                        best, best_d, i = ids[k], d, k
+            elif ids:
                 dr, dc = c[0] - pos[:, 0], c[1] - pos[:, 1]
                 d = np.sqrt(dr * dr + dc * dc + ev[0] * ev[0] + ev[1] * ev[1])
-                d[np.isnan(d)] = np.inf          # a NaN distance never matches (d < best_d is false in the loop form)
-                i = int(np.argmin(d))            # the first of equal minima, like the strict < of the loop
+                d[np.isnan(d)] = np.inf
+                i = int(np.argmin(d))
                 if d[i] < self.gamma:
                     best = ids[i]
             if best is not None:
@@ -90,7 +103,7 @@ class TrackManager:
                 self._predict(t, dt, z[2], z[3])
                 self._update(t, z)
                 new[best] = t
-                pos[i, 0], pos[i, 1] = t.state[0], t.state[1]
+                pos[i][0], pos[i][1] = float(t.state[0]), float(t.state[1])
             else:
                 new.setdefault(next_id, None)    # keeps the position of the first unmatched cluster in the dict
                 last_new = cl["measurement"]
