@@ -720,9 +720,11 @@ def run_cfg5(args):
     for k in range(args.warmup + 1):      # tick 0 only rasterises (no pair yet)
         tick(k)
     barrier()
-    eng.profile(True)
-    eng.profile_reset()
-    launches0 = eng.launch_count()
+    engines = [eng] + list(runner.pre_engines)     # the sweeps' cloud -> BEV chains run on engines of their own
+    for e in engines:
+        e.profile(True)
+        e.profile_reset()
+    launches0 = sum(e.launch_count() for e in engines)
     lat, gather_ms, stage = [], [], dict(preprocess=0.0, flow_to_summaries=0.0, tracker=0.0)
     done = tracks = 0
     sampler.mark_begin()
@@ -738,9 +740,14 @@ def run_cfg5(args):
     barrier()
     wall = time.perf_counter() - t_begin
     sampler.mark_end()
-    prof = eng.profile_read()
-    eng.profile(False)
-    launches = eng.launch_count() - launches0
+    prof = {}
+    for e in engines:
+        for key, v in e.profile_read().items():
+            acc = prof.setdefault(key, dict(ms=0.0, launches=0))
+            acc["ms"] += v["ms"]
+            acc["launches"] += v["launches"]
+        e.profile(False)
+    launches = sum(e.launch_count() for e in engines) - launches0
     t = torch.tensor([wall, max(lat), float(np.quantile(lat, 0.99))], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([done, launches, tracks], dtype=torch.int64, device="cuda")
     if world > 1:

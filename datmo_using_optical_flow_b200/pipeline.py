@@ -15,7 +15,7 @@ from __future__ import annotations
 
 from . import artefacts
 from . import main as ops
-from .engine import default_engine
+from .engine import Engine, default_engine
 from .tracker import TrackManager
 
 # the reference's config.yaml keys that the loop reads (main.py:542-550)
@@ -120,7 +120,7 @@ class SequenceRunner:
     per sequence."""
 
     def __init__(self, sequence_ids, config=None, engine=None, seed: int = 0, max_clusters: int = 512,
-                 cap: int | None = None, keep_cells: bool = False, ground_masks=None):
+                 cap: int | None = None, keep_cells: bool = False, ground_masks=None, pre_streams: int | None = None):
         import torch
         self.torch = torch
         self.cfg = dict(DEFAULT_CONFIG)
@@ -133,6 +133,17 @@ class SequenceRunner:
         self.keep_cells = bool(keep_cells)
         self.ground_masks = ground_masks     # optional {sequence id: [per-frame uint8 masks]} instead of RANSAC
         self.trackers = [TrackManager() for _ in range(self.n)]
+        # The sweeps of one tick are independent: their cloud -> BEV chains (a dozen short, latency-bound kernels
+        # around one long one, per sweep) run on a few engines of their own — own handle, stream and workspace —
+        # so that they overlap on the GPU; the batched flow -> clusters call then waits for all of them.
+        # datmo_preprocess_dev blocks its caller until the sweep's point count is known (an empty ROI is a return
+        # code), so each engine is driven by a host thread of its own; ctypes drops the GIL for the call.
+        k = min(4, self.n) if pre_streams is None else int(pre_streams)
+        self.pre_engines = [Engine(self.eng.device, isolated=True) for _ in range(k)] if k > 1 else []
+        self._pool = None
+        if self.pre_engines:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=k, thread_name_prefix="datmo-pre")
         self.prev = [None] * self.n          # device BEV of the previous tick, per sequence
         self.frame = 0
         eng, cfg = self.eng, self.cfg
@@ -144,21 +155,32 @@ class SequenceRunner:
         self.py = (cfg["y_range"][1] - cfg["y_range"][0]) / self.nx
         self.last_ms = {}
 
+    def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        for pe in self.pre_engines:
+            pe.close()
+        self.pre_engines = []
+
     def _bev(self, j: int, cloud):
-        torch, eng, cfg = self.torch, self.eng, self.cfg
+        torch, cfg = self.torch, self.cfg
+        eng = self.pre_engines[j % len(self.pre_engines)] if self.pre_engines else self.eng
         if cloud is None:
             return None
         try:
-            pts = cloud if isinstance(cloud, torch.Tensor) else torch.from_numpy(cloud)
-            pts = pts.to(eng.tdev, dtype=torch.float32, non_blocking=True)
-            if pts.shape[1] == 3:
-                pts = torch.cat([pts, torch.zeros_like(pts[:, :1])], dim=1)
-            gm = None
-            if self.ground_masks is not None:
-                gm = torch.as_tensor(self.ground_masks[self.ids[j]][self.frame]).to(eng.tdev)
-            # the same seed process_clouds(seed=seed + 1000 * id) gives frame `self.frame` of this sequence
-            return eng.preprocess(pts, cfg["grid_resolution"], cfg["x_range"], cfg["y_range"], cfg["z_max"],
-                                  cfg["roi_bounds"], seed=self.seed + 1000 * self.ids[j] + self.frame, ground_mask=gm)
+            with eng.on_stream():       # the upload too runs on the engine's stream (an isolated engine orders nothing)
+                pts = cloud if isinstance(cloud, torch.Tensor) else torch.from_numpy(cloud)
+                pts = pts.to(eng.tdev, dtype=torch.float32, non_blocking=True)
+                if pts.shape[1] == 3:
+                    pts = torch.cat([pts, torch.zeros_like(pts[:, :1])], dim=1)
+                gm = None
+                if self.ground_masks is not None:
+                    gm = torch.as_tensor(self.ground_masks[self.ids[j]][self.frame]).to(eng.tdev)
+                # the same seed process_clouds(seed=seed + 1000 * id) gives frame `self.frame` of this sequence
+                return eng.preprocess(pts, cfg["grid_resolution"], cfg["x_range"], cfg["y_range"], cfg["z_max"],
+                                      cfg["roi_bounds"], seed=self.seed + 1000 * self.ids[j] + self.frame,
+                                      ground_mask=gm)
         except Exception:       # the reference prints and moves on (main.py:635-637)
             return None
 
@@ -169,7 +191,21 @@ class SequenceRunner:
         if len(clouds) != self.n:
             raise ValueError(f"expected {self.n} sweeps, one per sequence")
         t0 = time.perf_counter()
-        bevs = [self._bev(j, c) for j, c in enumerate(clouds)]
+        if self._pool is not None:
+            k = len(self.pre_engines)
+
+            def group(e):       # one thread per engine: the sweeps e, e + k, .. in order
+                with torch.cuda.device(self.eng.device):
+                    return [(j, self._bev(j, clouds[j])) for j in range(e, self.n, k)]
+
+            bevs = [None] * self.n
+            for part in self._pool.map(group, range(k)):
+                for j, b in part:
+                    bevs[j] = b
+        else:
+            bevs = [self._bev(j, c) for j, c in enumerate(clouds)]
+        for pe in self.pre_engines:     # host-side join: the BEVs are complete before the batched call reads them
+            pe.synchronize()
         eng.synchronize()
         t1 = time.perf_counter()
         live = [j for j in range(self.n) if self.prev[j] is not None and bevs[j] is not None]
@@ -230,10 +266,13 @@ def process_sequences(sequences, config=None, engine=None, seed=0, max_clusters=
     runner = SequenceRunner(local, config, engine, seed=seed, max_clusters=max_clusters, ground_masks=ground_masks)
     n_ticks = len(sequences[0]) if sequences else 0
     ticks, gathered = [], []
-    for k in range(n_ticks):
-        recs = runner.tick([sequences[s][k] for s in local])
-        ticks.append(recs)
-        if gather:
-            tables = {s: runner.trackers[j].as_array() for j, s in enumerate(local)}
-            gathered.append(sharding.gather_sequence_tracks(tables, len(sequences), max_tracks))
+    try:
+        for k in range(n_ticks):
+            recs = runner.tick([sequences[s][k] for s in local])
+            ticks.append(recs)
+            if gather:
+                tables = {s: runner.trackers[j].as_array() for j, s in enumerate(local)}
+                gathered.append(sharding.gather_sequence_tracks(tables, len(sequences), max_tracks))
+    finally:
+        runner.close()      # the helper engines and their host threads; trackers and records stay usable
     return dict(local=local, ticks=ticks, gathered=gathered, runner=runner)
