@@ -73,8 +73,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up until after the
-    timed region; stop() keeps the samples whose timestamps fall inside the timed region."""
+    """SM clock / throttle reasons from before the warm-up until after the timed region; stop() keeps the samples
+    whose timestamps fall inside the timed region.  NVML from a thread of this process every 4 ms (a call is
+    ~50 us and drops the GIL), so that even a 90 ms timed region holds ~20 samples; `nvidia-smi -lms 20` in a
+    child process when NVML cannot be loaded."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -85,7 +87,40 @@ class ClockSampler:
         self.path = None
         self.t0 = self.t1 = None
 
+    def _start_nvml(self) -> bool:
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)      # fails here, not in the thread
+            reasons_fn(h)
+            self.rows, self._halt = [], threading.Event()
+
+            def loop():
+                while not self._halt.is_set():
+                    try:
+                        r = int(reasons_fn(h))
+                        self.rows.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), mx,
+                                          [n for n, b in bits.items() if r & b]))
+                    except Exception:
+                        pass
+                    self._halt.wait(0.004)
+
+            self._thread = threading.Thread(target=loop, name="clock-sampler", daemon=True)
+            self._thread.start()
+            return True
+        except Exception:
+            return False
+
     def start(self):
+        self._thread = None
+        if not os.environ.get("DATMO_CLOCKS_NVIDIA_SMI") and self._start_nvml():
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -102,6 +137,11 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self) -> dict:
+        if self._thread is not None:
+            time.sleep(0.01)
+            self._halt.set()
+            self._thread.join(timeout=2)
+            return self._summary(list(self.rows), "nvml")
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
@@ -124,6 +164,9 @@ class ClockSampler:
                 except ValueError:
                     continue
         os.unlink(self.path)
+        return self._summary(rows, "nvidia-smi")
+
+    def _summary(self, rows, source) -> dict:
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         window = "timed region"
@@ -134,7 +177,7 @@ class ClockSampler:
             inside, window = rows, "whole run (timed region shorter than the sampling period)"
         reasons = sorted({n for r in inside for n in r[3]})
         return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
-                "reasons": reasons, "samples": len(inside), "window": window}
+                "reasons": reasons, "samples": len(inside), "window": window, "source": source}
 
 
 # ------------------------------------------------------------------------------------------------
