@@ -1857,9 +1857,19 @@ __device__ __forceinline__ void xm_v_phase(const float* sM, float* sV, int vpos0
 // horizontal sums over the 46-column window, in place: the 32 finished columns land on window
 // columns 14..45 (where the next group's vertical sums will be written after the solve has read
 // them) and the last 14 window columns move to the front
+// fill: columns outside the image are replicas of the edge column (replicate border), so their vertical sums are
+// copies of the edge column's — the thread that owns a row writes them before it sums the row, instead of a
+// lead-in / tail group evaluating M for them.  fill_n values from window column fill_src to fill_dst.. (0: none)
 template <typename T>
-__device__ __forceinline__ void xm_h_phase(float* sV, int tid) {
-    for (int i = tid; i < 5 * T::TY; i += T::NT) window_sums_carry<T::WIN, 32>(sV + i * T::VS);  // i = c * TY + row
+__device__ __forceinline__ void xm_h_phase(float* sV, int tid, int fill_src = 0, int fill_dst = 0, int fill_n = 0) {
+    for (int i = tid; i < 5 * T::TY; i += T::NT) {   // i = c * TY + row
+        float* v = sV + i * T::VS;
+        if (fill_n) {
+            const float e = v[fill_src];
+            for (int j = 0; j < fill_n; ++j) v[fill_dst + j] = e;
+        }
+        window_sums_carry<T::WIN, 32>(v);
+    }
 }
 
 // 2x2 solve on the raw window sums: norm^2 scales the determinant and both numerators alike
@@ -1887,7 +1897,7 @@ __global__ void __launch_bounds__(T::NT, T::MINB) k_flow_iter_xm(const float* __
                                                                  const float* __restrict__ R1,
                                                                  const float2* __restrict__ flow_in,
                                                                  float2* __restrict__ flow_out, int w, int h, int seg,
-                                                                 float norm, int prefetch) {
+                                                                 float norm, int prefetch, int edge_fill) {
     extern __shared__ float sM[];     // [5][RH][MS]
     float* sV = sM + T::M_FLOATS;     // [5][TY][VS]
     const int x0 = blockIdx.x * seg, y0 = blockIdx.y * T::TY, b = blockIdx.z;
@@ -1903,21 +1913,33 @@ __global__ void __launch_bounds__(T::NT, T::MINB) k_flow_iter_xm(const float* __
     const float2* fb = flow_in + static_cast<size_t>(b) * plane;
     float2* fo = flow_out + static_cast<size_t>(b) * plane;
     // k = -1: lead-in, the 8 columns left of the segment (only the last 7 are read) -> window columns
-    // 6..13; k = ngroups: tail, the 8 columns right of it that finish its last 7 outputs
+    // 6..13; k = ngroups: tail, the 8 columns right of it that finish its last 7 outputs.  At the image's
+    // left / right edge those columns are replicas of column 0 / w - 1: no M, no vertical sums — the H phase
+    // copies the edge column's sums (bit-identical: the replicas' M values are the edge column's).
     for (int k = -1; k <= ngroups; ++k) {
         const bool lead = k < 0, tail = k == ngroups;
         const int c0 = lead ? x0 - 8 : x0 + 32 * k;
         if (tail && c0 - T::HM >= xhi) break;
+        if (lead && x0 == 0 && edge_fill) continue;
         const int ncl2 = (lead || tail) ? 3 : 5;
-        // M(k) may start as soon as V(k-1) has left sM: the barrier in front of H(k-1) saw to that,
-        // so the solve of group k-1 and this M phase share one barrier interval
-        if (prefetch && k + 1 < ngroups) xm_prefetch<T>(r0q, r0s, r1q, r1s, fb, w, h, x0 + 32 * (k + 1), ry0);
-        xm_m_phase<T>(sM, r0q, r0s, r1q, r1s, fb, w, h, c0, ry0, ncl2);
-        __syncthreads();  // M complete; S(k-1) has read the window columns V(k) overwrites
-        xm_v_phase<T>(sM, sV, lead ? 6 : 14, ncl2, threadIdx.x);
-        __syncthreads();
+        // window columns 0..13 hold columns c0 - 14 .. c0 - 1; at the right edge column w - 1 is one of the last 7
+        const bool rep_tail = tail && c0 >= w && edge_fill;
+        if (!rep_tail) {
+            // M(k) may start as soon as V(k-1) has left sM: the barrier in front of H(k-1) saw to that,
+            // so the solve of group k-1 and this M phase share one barrier interval
+            if (prefetch && k + 1 < ngroups) xm_prefetch<T>(r0q, r0s, r1q, r1s, fb, w, h, x0 + 32 * (k + 1), ry0);
+            xm_m_phase<T>(sM, r0q, r0s, r1q, r1s, fb, w, h, c0, ry0, ncl2);
+            __syncthreads();  // M complete; S(k-1) has read the window columns V(k) overwrites
+            xm_v_phase<T>(sM, sV, lead ? 6 : 14, ncl2, threadIdx.x);
+        }
+        __syncthreads();      // (replica tail: S(k-1) has read the window columns the fill overwrites)
         if (lead) continue;
-        xm_h_phase<T>(sV, threadIdx.x);
+        int fill_src = 0, fill_dst = 0, fill_n = 0;
+        if (rep_tail)
+            fill_src = w + 13 - c0, fill_dst = 14, fill_n = 8;      // columns w .. = column w - 1
+        else if (k == 0 && x0 == 0 && edge_fill)
+            fill_src = 14, fill_dst = 7, fill_n = 7;                // columns -7 .. -1 = column 0
+        xm_h_phase<T>(sV, threadIdx.x, fill_src, fill_dst, fill_n);
         __syncthreads();
         xm_solve<T>(sV, fo, w, h, y0, c0, x0, xhi, norm, threadIdx.x);
     }
@@ -2177,12 +2199,13 @@ int launch_flow_iter_xm(datmo_ctx* h, const float* R0, const float* R1, const fl
     static SmemGrant grant;
     DATMO_TRY(datmo_grant_smem(h, k_flow_iter_xm<T>, T::SMEM, grant));
     static const int prefetch = getenv("DATMO_XM_PREFETCH") ? atoi(getenv("DATMO_XM_PREFETCH")) : 1;
+    static const int edge_fill = getenv("DATMO_XM_EDGE_FILL") ? atoi(getenv("DATMO_XM_EDGE_FILL")) : 1;   // A/B switch
     dim3 g(ceil_div(w, seg), ceil_div(hh, T::TY), B);
     {
         LaunchScope ls(h, DATMO_TAG_FLOW_ITER);
         k_flow_iter_xm<T><<<g, T::NT, T::SMEM, h->stream>>>(R0, R1, reinterpret_cast<const float2*>(flow_in),
                                                            reinterpret_cast<float2*>(flow_out), w, hh, seg, norm,
-                                                           prefetch);
+                                                           prefetch, edge_fill);
     }
     DATMO_POST_LAUNCH(h);
     return DATMO_OK;
